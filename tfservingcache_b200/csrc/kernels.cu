@@ -1,0 +1,318 @@
+// Executor kernels for sm_100a (B200). fp32 SIMT: the per-tenant models of the Zipf mix are run
+// at batch <= 8 rows per pass, where y = xW + b is bound by streaming W from HBM once
+// (intensity rows/2 FLOP/B, far below the fp32 ridge) -- so the design goal is HBM-rate
+// streaming: 128-bit coalesced loads, >= 64 KB in flight per SM, one CTA per SM-sized grid,
+// x staged in shared memory and broadcast, deterministic split-K reduction by the last CTA of
+// each column strip (no float atomics: bit-reproducible results).
+#include "kernels.h"
+
+#include <atomic>
+
+namespace tfsc {
+
+static std::atomic<int64_t> g_launches{0};
+int64_t kernel_launch_count() { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------ X1 ----
+__global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n,
+                                                     const float* __restrict__ pa, const float* __restrict__ pb) {
+  const float a = __ldg(pa), b = __ldg(pb);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (vec) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (int64_t j = i; j < n4; j += stride) {
+      float4 v = __ldg(x4 + j);
+      v.x = fmaf(a, v.x, b); v.y = fmaf(a, v.y, b); v.z = fmaf(a, v.z, b); v.w = fmaf(a, v.w, b);
+      y4[j] = v;
+    }
+    for (int64_t j = (n4 << 2) + i; j < n; j += stride) y[j] = fmaf(a, x[j], b);
+  } else {
+    for (int64_t j = i; j < n; j += stride) y[j] = fmaf(a, x[j], b);
+  }
+}
+
+cudaError_t launch_affine(const float* x, float* y, int64_t n, const float* a, const float* b, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  affine_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, y, n, a, b);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ X2 ----
+// Tile geometry: a CTA owns a strip of kStripCols columns (2 KB of every W row: long contiguous
+// DRAM bursts) and one of `splits` K-chunks. 512 threads = 128 float4 columns x 4 k-lanes; every
+// thread keeps kUnroll independent 16-byte loads in flight (64 KB per CTA).
+constexpr int kThreads = 512;
+constexpr int kColsPerThread = 8;                          // one 256-bit load (LDG.E.256, new on sm_100)
+constexpr int kColGroups = 64;                             // 32-byte column groups per strip
+constexpr int kStripCols = kColGroups * kColsPerThread;    // 512
+constexpr int kKLanes = kThreads / kColGroups;             // 8
+constexpr int kUnroll = 4;
+constexpr int kMaxChunkK = 4096;                           // x chunk rows staged in smem (8 * 4096 * 4 B = 128 KB)
+
+struct __align__(32) float8 { float v[8]; };
+
+// streaming 32-byte load: no L1 allocation, L2 evict-first (W is read exactly once per pass)
+__device__ __forceinline__ float8 ld_stream(const float8* p) {
+  float8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
+                 "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
+// Workspace layout: [strips] uint32 arrival counters (self-resetting), then partial sums
+// float[strips][splits][R][kStripCols].
+template <int R>
+__global__ void __launch_bounds__(kThreads, 1)
+dense_stream_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                    float* __restrict__ y, int rows, int K, int N, int relu, int splits, int chunk_k,
+                    unsigned int* __restrict__ counters, float* __restrict__ partials) {
+  extern __shared__ __align__(32) float smem[];
+  float* xs = smem;  // [chunk_k][R]  (k-major so a broadcast LDS.128 yields 4 rows of the batch)
+
+  const int strip = blockIdx.x;
+  const int split = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int cg = tid % kColGroups;
+  const int kl = tid / kColGroups;
+  const int col0 = strip * kStripCols + cg * kColsPerThread;
+  const bool col_ok = col0 < N;  // N % 8 == 0 guaranteed by the host
+  const int k_begin = split * chunk_k;
+  const int k_end = min(K, k_begin + chunk_k);
+  const int kc = max(0, k_end - k_begin);
+
+  // stage x[:, k_begin:k_end] transposed into smem: xs[k][r]
+  for (int idx = tid; idx < kc * R; idx += kThreads) {
+    const int r = idx / kc, k = idx - r * kc;
+    xs[k * R + r] = (r < rows) ? __ldg(x + (size_t)r * K + k_begin + k) : 0.f;
+  }
+  __syncthreads();
+
+  float acc[R][kColsPerThread];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c < kColsPerThread; ++c) acc[r][c] = 0.f;
+
+  if (col_ok) {
+    const float8* wp = reinterpret_cast<const float8*>(w + (size_t)(k_begin + kl) * N + col0);
+    const size_t row_stride8 = (size_t)N / 8 * kKLanes;  // float8 units between this thread's rows
+    int k = kl;
+    // main loop: kUnroll rows per iteration, all loads issued before the first use
+    for (; k + (kUnroll - 1) * kKLanes < kc; k += kUnroll * kKLanes) {
+      float8 wv[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) wv[u] = ld_stream(wp + (size_t)u * row_stride8);
+      wp += (size_t)kUnroll * row_stride8;
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const float* xr = xs + (k + u * kKLanes) * R;
+        float xv[R];
+        if (R % 4 == 0) {
+#pragma unroll
+          for (int q = 0; q < R / 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(xr + 4 * q);
+            xv[4 * q + 0] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w;
+          }
+        } else if (R == 2) {
+          const float2 t = *reinterpret_cast<const float2*>(xr);
+          xv[0] = t.x; xv[1] = t.y;
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) xv[r] = xr[r];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < kColsPerThread; ++c) acc[r][c] = fmaf(xv[r], wv[u].v[c], acc[r][c]);
+      }
+    }
+    for (; k < kc; k += kKLanes) {  // tail rows
+      const float8 wv = ld_stream(wp);
+      wp += row_stride8;
+      const float* xr = xs + k * R;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float xv = xr[r];
+#pragma unroll
+        for (int c = 0; c < kColsPerThread; ++c) acc[r][c] = fmaf(xv, wv.v[c], acc[r][c]);
+      }
+    }
+  }
+
+  // intra-CTA reduction over the k-lanes (fixed order -> deterministic), through smem
+  __syncthreads();  // xs no longer needed
+  float* red = smem;  // [kKLanes][R][kStripCols]
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    float4* dst = reinterpret_cast<float4*>(red + ((size_t)(kl * R + r) * kStripCols) + cg * kColsPerThread);
+    dst[0] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    dst[1] = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+  }
+  __syncthreads();
+
+  constexpr int kVecPerRow = kStripCols / 4;  // float4 per strip row
+  const float4* red4 = reinterpret_cast<const float4*>(red);
+  float4* my_partial = reinterpret_cast<float4*>(partials + ((size_t)(strip * splits + split) * R) * kStripCols);
+  for (int idx = tid; idx < R * kVecPerRow; idx += kThreads) {
+    const int r = idx / kVecPerRow, c = idx - r * kVecPerRow;
+    float4 s = red4[(size_t)(0 * R + r) * kVecPerRow + c];
+#pragma unroll
+    for (int l = 1; l < kKLanes; ++l) {
+      const float4 t = red4[(size_t)(l * R + r) * kVecPerRow + c];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    if (splits == 1) {
+      const int col = strip * kStripCols + c * 4;
+      if (r < rows && col < N) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+        s.x += bv.x; s.y += bv.y; s.z += bv.z; s.w += bv.w;
+        if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+        *reinterpret_cast<float4*>(y + (size_t)r * N + col) = s;
+      }
+    } else {
+      my_partial[r * kVecPerRow + c] = s;
+    }
+  }
+  if (splits == 1) return;
+
+  // last CTA of this strip folds the `splits` partials in split order, adds bias, activation
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(&counters[strip], 1u);
+    s_last = (prev == (unsigned)splits - 1) ? 1u : 0u;
+    if (s_last) counters[strip] = 0u;  // self-reset for the next launch on this stream
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float4* strip_partials = reinterpret_cast<const float4*>(partials + (size_t)strip * splits * R * kStripCols);
+  for (int idx = tid; idx < R * kVecPerRow; idx += kThreads) {
+    const int r = idx / kVecPerRow, c = idx - r * kVecPerRow;
+    const int col = strip * kStripCols + c * 4;
+    if (r >= rows || col >= N) continue;
+    float4 s = __ldcg(strip_partials + (size_t)(0 * R + r) * kVecPerRow + c);
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 t = __ldcg(strip_partials + (size_t)(sp * R + r) * kVecPerRow + c);
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+    s.x += bv.x; s.y += bv.y; s.z += bv.z; s.w += bv.w;
+    if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+    *reinterpret_cast<float4*>(y + (size_t)r * N + col) = s;
+  }
+}
+
+// Generic fallback for shapes the streaming kernel does not cover (N % 8 != 0 or unaligned W):
+// one thread per output column, coalesced across columns. Small models only.
+__global__ void __launch_bounds__(256)
+dense_generic_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     float* __restrict__ y, int rows, int K, int N, int relu) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (n >= N || r >= rows) return;
+  float acc = 0.f;
+  const float* xr = x + (size_t)r * K;
+  for (int k = 0; k < K; ++k) acc = fmaf(__ldg(xr + k), __ldg(w + (size_t)k * N + n), acc);
+  acc += __ldg(bias + n);
+  if (relu) acc = fmaxf(acc, 0.f);
+  y[(size_t)r * N + n] = acc;
+}
+
+struct DensePlan {
+  int strips, splits, chunk_k;
+};
+
+static DensePlan plan_dense(int k, int n) {
+  DensePlan p;
+  p.strips = (n + kStripCols - 1) / kStripCols;
+  // fill ~one CTA per SM (148 on B200); each chunk must fit the smem x stage
+  int splits = 148 / p.strips;
+  if (splits < 1) splits = 1;
+  int min_splits = (k + kMaxChunkK - 1) / kMaxChunkK;
+  if (splits < min_splits) splits = min_splits;
+  if (splits > k / 64 && k >= 64) splits = k / 64;  // keep chunks >= 64 rows
+  if (splits < 1) splits = 1;
+  int chunk = (k + splits - 1) / splits;
+  chunk = (chunk + kKLanes - 1) / kKLanes * kKLanes;
+  p.chunk_k = chunk;
+  p.splits = (k + chunk - 1) / chunk;
+  return p;
+}
+
+size_t dense_workspace_bytes(int rows, int k, int n) {
+  (void)rows;
+  DensePlan p = plan_dense(k, n);
+  size_t counters = ((size_t)p.strips * sizeof(unsigned int) + 255) & ~(size_t)255;
+  size_t partials = (size_t)p.strips * p.splits * kMaxRowsPerLaunch * kStripCols * sizeof(float);
+  return counters + partials;
+}
+
+template <int R>
+static cudaError_t launch_dense_r(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n,
+                                  bool relu, void* workspace, const DensePlan& p, cudaStream_t s) {
+  size_t xs_bytes = (size_t)p.chunk_k * R * sizeof(float);
+  size_t red_bytes = (size_t)kKLanes * R * kStripCols * sizeof(float);
+  size_t smem = xs_bytes > red_bytes ? xs_bytes : red_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(dense_stream_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  unsigned int* counters = static_cast<unsigned int*>(workspace);
+  size_t coff = ((size_t)p.strips * sizeof(unsigned int) + 255) & ~(size_t)255;
+  float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + coff);
+  dim3 grid(p.strips, p.splits);
+  dense_stream_kernel<R><<<grid, kThreads, smem, s>>>(x, w, bias, y, rows, k, n, relu ? 1 : 0, p.splits, p.chunk_k,
+                                                      counters, partials);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dense(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n,
+                         bool relu, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  if (rows <= 0 || n <= 0) return cudaSuccess;
+  const bool stream_ok = (n % 8 == 0) && ((reinterpret_cast<uintptr_t>(w) & 31) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(bias) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                         k >= 1 && workspace && workspace_bytes >= dense_workspace_bytes(rows, k, n);
+  if (!stream_ok) {
+    for (int r0 = 0; r0 < rows; r0 += 65535) {
+      int rr = rows - r0 < 65535 ? rows - r0 : 65535;
+      dim3 grid((n + 255) / 256, rr);
+      dense_generic_kernel<<<grid, 256, 0, s>>>(x + (size_t)r0 * k, w, bias, y + (size_t)r0 * n, rr, k, n, relu ? 1 : 0);
+      g_launches++;
+    }
+    return cudaGetLastError();
+  }
+  const DensePlan p = plan_dense(k, n);
+  for (int r0 = 0; r0 < rows; r0 += kMaxRowsPerLaunch) {
+    const int rr = rows - r0 < kMaxRowsPerLaunch ? rows - r0 : kMaxRowsPerLaunch;
+    const float* xp = x + (size_t)r0 * k;
+    float* yp = y + (size_t)r0 * n;
+    cudaError_t e;
+    if (rr == 1) e = launch_dense_r<1>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+    else if (rr == 2) e = launch_dense_r<2>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+    else if (rr <= 4) e = launch_dense_r<4>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+    else e = launch_dense_r<8>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace tfsc
+
+extern "C" {
+int64_t tfsc_kernel_launches(void) { return tfsc::kernel_launch_count(); }
+}

@@ -1,0 +1,24 @@
+// Device kernels of the executor. All fp32, sm_100a.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace tfsc {
+
+constexpr int kMaxRowsPerLaunch = 8;  // rows handled by one streaming pass over W (SIMT path)
+
+// X1: y = a*x + b (a, b device scalars). half_plus_two (deploy/docker-compose/readme.md:40-42).
+cudaError_t launch_affine(const float* x, float* y, int64_t n, const float* a, const float* b, cudaStream_t s);
+
+// X2: y[rows,n] = act(x[rows,k] W[k,n] + bias[n]); W row-major [k,n]. Streams W exactly once per
+// group of <= kMaxRowsPerLaunch rows. workspace: dense_workspace_bytes(rows,k,n), zero-initialised
+// counters are maintained by the kernel itself (self-resetting).
+size_t dense_workspace_bytes(int rows, int k, int n);
+cudaError_t launch_dense(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n,
+                         bool relu, void* workspace, size_t workspace_bytes, cudaStream_t s);
+
+int64_t kernel_launch_count();
+
+}  // namespace tfsc

@@ -1,0 +1,51 @@
+// Model bundle description ("tfsc-b200-v1"): what the provider hands to the cache manager and
+// what the executor runs. A bundle is <baseDir>/<name>/<version>/{tfsc_model.json, weights.bin};
+// weights.bin is copied verbatim into pinned host memory and from there into the HBM arena, so
+// offsets in the manifest are valid in all three places (256-byte aligned tensors).
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "json.h"
+
+namespace tfsc {
+
+enum class Template { Affine, Mlp };
+
+struct DenseLayer {
+  int in = 0, out = 0;
+  bool relu = false;
+  size_t w_off = 0, b_off = 0;  // bytes into the blob; W row-major [in,out] fp32, b[out]
+};
+
+struct ModelDesc {
+  Template tmpl = Template::Mlp;
+  std::vector<DenseLayer> layers;  // Mlp
+  size_t a_off = 0, b_off = 0;     // Affine scalars
+  size_t weights_bytes = 0;
+  std::string input_name = "x", output_name = "y";
+  // elements per batch row; 0 = elementwise / any shape (Affine)
+  int64_t in_dim = 0, out_dim = 0;
+  int max_width = 0;  // widest activation (for scratch sizing)
+};
+
+bool parse_manifest(const Json& j, ModelDesc* d, std::string* err);
+ModelDesc make_mlp_desc(const std::vector<int>& dims, const std::vector<std::string>& activations);
+ModelDesc make_affine_desc();
+std::string manifest_json(const ModelDesc& d);
+
+// A model held in the host tier (pinned memory when a CUDA device is present).
+struct HostModel {
+  ModelId id;
+  ModelDesc desc;
+  void* data = nullptr;
+  size_t bytes = 0;
+  std::function<void(void*, size_t)> release;  // returns the block to its pool
+  ~HostModel() {
+    if (data && release) release(data, bytes);
+  }
+};
+
+}  // namespace tfsc

@@ -1,0 +1,768 @@
+#include "node.h"
+
+#include <chrono>
+#include <set>
+
+#include "kernels.h"
+
+namespace tfsc {
+
+using Clock = std::chrono::steady_clock;
+static double secs_since(Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
+
+#define CU_OK(expr, errp, code)                                                        \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      if (errp) *(errp) = std::string(#expr) + ": " + cudaGetErrorString(_e);          \
+      return code;                                                                     \
+    }                                                                                  \
+  } while (0)
+
+Node::Node(const NodeConfig& cfg, ModelProvider* provider)
+    : cfg_(cfg), provider_(provider), lru_("", cfg.host_cache_bytes) {
+  lru_.on_evict = [this](const CachedModel& m) { on_host_evict_locked(m); };
+}
+
+bool Node::init(std::string* err) {
+  DeviceGuard g(cfg_.device);
+  CU_OK(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking), err, false);
+  CU_OK(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking), err, false);
+  size_t bytes = (size_t)cfg_.arena_bytes;
+  if (bytes == 0) {
+    size_t fr = 0, tot = 0;
+    CU_OK(cudaMemGetInfo(&fr, &tot), err, false);
+    bytes = (size_t)(fr * 0.85);
+  }
+  CU_OK(cudaMalloc(&slab_, bytes), err, false);
+  arena_.init(bytes, 1024);
+  slots_.resize(cfg_.slots > 0 ? cfg_.slots : 1);
+  for (auto& s : slots_) CU_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), err, false);
+  batcher_ = std::thread([this] { batcher_loop(); });
+  completer_ = std::thread([this] { completer_loop(); });
+  return true;
+}
+
+Node::~Node() {
+  {
+    std::lock_guard<std::mutex> lk(q_mu_);
+    stop_ = true;
+  }
+  q_cv_.notify_all();
+  slot_cv_.notify_all();
+  if (batcher_.joinable()) batcher_.join();
+  if (completer_.joinable()) completer_.join();
+  DeviceGuard g(cfg_.device);
+  cudaDeviceSynchronize();
+  for (auto& s : slots_) {
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.h_out) cudaFreeHost(s.h_out);
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.act0) cudaFree(s.act0);
+    if (s.act1) cudaFree(s.act1);
+    if (s.ws) cudaFree(s.ws);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  for (auto& kv : stream_scratch_) cudaFree(kv.second.base);
+  for (auto& r : retire_) cudaEventDestroy(r.ev);
+  for (auto& kv : dev_)
+    if (kv.second->ready) cudaEventDestroy(kv.second->ready);
+  dev_.clear();
+  host_.clear();  // returns pinned blocks to the pool
+  for (auto e : event_pool_) cudaEventDestroy(e);
+  for (auto& kv : pool_)
+    for (void* p : kv.second) cudaFreeHost(p);
+  if (slab_) cudaFree(slab_);
+  if (compute_) cudaStreamDestroy(compute_);
+  if (copy_) cudaStreamDestroy(copy_);
+}
+
+cudaEvent_t Node::get_event() {
+  if (!event_pool_.empty()) {
+    cudaEvent_t e = event_pool_.back();
+    event_pool_.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  return e;
+}
+void Node::put_event(cudaEvent_t e) { event_pool_.push_back(e); }
+
+void* Node::host_alloc(size_t bytes, std::function<void(void*, size_t)>* release) {
+  void* p = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(pool_mu_);
+    auto it = pool_.find(bytes);
+    if (it != pool_.end() && !it->second.empty()) {
+      p = it->second.back();
+      it->second.pop_back();
+    }
+  }
+  if (!p) {
+    DeviceGuard g(cfg_.device);
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+  }
+  *release = [this](void* q, size_t n) {
+    std::lock_guard<std::mutex> lk(pool_mu_);
+    auto& v = pool_[n];
+    if (v.size() < 8) v.push_back(q);  // exact-size reuse: pinning 1 GB costs ~100 ms, reuse is free
+    else cudaFreeHost(q);
+  };
+  return p;
+}
+
+// ------------------------------------------------------------------ residency machine ------
+std::vector<CachedModel> Node::resident_prefix_locked() {
+  // cachemanager.go:168-169: first min(len, MaxConcurrentModels) of the MRU list, additionally
+  // cut where the HBM arena byte budget would be exceeded.
+  std::vector<CachedModel> all = lru_.list_models();
+  std::vector<CachedModel> out;
+  size_t used = 0;
+  for (auto& m : all) {
+    if ((int)out.size() >= cfg_.max_concurrent_models) break;
+    size_t need = ((size_t)m.size_on_disk + 1023) / 1024 * 1024;
+    if (used + need > arena_.capacity()) break;
+    used += need;
+    out.push_back(m);
+  }
+  return out;
+}
+
+void Node::refresh_state_locked(DeviceModel* d) {
+  if (d->state == TFSC_STATE_LOADING && d->ready && cudaEventQuery(d->ready) == cudaSuccess) {
+    d->state = TFSC_STATE_AVAILABLE;
+    d->ready_seen = true;
+  } else {
+    cudaGetLastError();  // clear cudaErrorNotReady
+  }
+}
+
+void Node::release_locked(const std::shared_ptr<DeviceModel>& d) {
+  if (!d->dptr) return;
+  if (!d->ready_seen && d->ready) cudaEventSynchronize(d->ready);  // page-in DMA must not outlive its source
+  arena_.release(d->off);
+  d->dptr = nullptr;
+  d->state = TFSC_STATE_END;
+  d->host.reset();
+  if (d->ready) {
+    put_event(d->ready);
+    d->ready = nullptr;
+  }
+  ++ev_hbm_;
+  cv_.notify_all();
+}
+
+void Node::begin_unload_locked(const std::shared_ptr<DeviceModel>& d) {
+  d->state = TFSC_STATE_UNLOADING;
+  if (d->inflight == 0) release_locked(d);
+}
+
+void Node::on_host_evict_locked(const CachedModel& m) {
+  ++ev_host_;
+  host_.erase(m.id);
+  auto it = dev_.find(m.id);
+  if (it != dev_.end() && (it->second->state == TFSC_STATE_AVAILABLE || it->second->state == TFSC_STATE_LOADING))
+    begin_unload_locked(it->second);
+}
+
+void Node::reap_locked() {
+  while (!retire_.empty()) {
+    cudaError_t q = cudaEventQuery(retire_.front().ev);
+    if (q != cudaSuccess) {
+      cudaGetLastError();
+      break;
+    }
+    auto r = retire_.front();
+    retire_.pop_front();
+    put_event(r.ev);
+    if (--r.dm->inflight == 0 && r.dm->state == TFSC_STATE_UNLOADING) release_locked(r.dm);
+  }
+}
+
+void Node::unpin(const std::shared_ptr<DeviceModel>& dm) {
+  std::lock_guard<std::mutex> lk(mu_);
+  if (--dm->inflight == 0 && dm->state == TFSC_STATE_UNLOADING) {
+    DeviceGuard g(cfg_.device);
+    release_locked(dm);
+  }
+}
+
+int Node::reload_locked(std::unique_lock<std::mutex>& lk, const ModelId& want, std::string* err) {
+  const auto deadline = Clock::now() + std::chrono::duration<double>(cfg_.fetch_timeout_s);
+  for (;;) {
+    reap_locked();
+    std::vector<CachedModel> prefix = resident_prefix_locked();
+    std::set<std::pair<std::string, int64_t>> keep;
+    bool want_in = false;
+    for (auto& m : prefix) {
+      keep.insert({m.id.name, m.id.version});
+      if (m.id == want) want_in = true;
+    }
+    if (!want_in) {
+      *err = "model " + want.name + ":" + std::to_string(want.version) + " does not fit the HBM arena (" +
+             std::to_string(arena_.capacity()) + " bytes) / serving.maxConcurrentModels";
+      return TFSC_E_EXHAUSTED;
+    }
+    // unload what fell out of the resident prefix (TF-Serving drops models absent from the new config)
+    for (auto& kv : dev_) {
+      auto& d = kv.second;
+      if ((d->state == TFSC_STATE_AVAILABLE || d->state == TFSC_STATE_LOADING) &&
+          !keep.count({d->id.name, d->id.version}))
+        begin_unload_locked(d);
+    }
+    // page in what is missing, MRU first
+    for (auto& m : prefix) {
+      auto it = dev_.find(m.id);
+      std::shared_ptr<DeviceModel> d = it == dev_.end() ? nullptr : it->second;
+      if (d && (d->state == TFSC_STATE_AVAILABLE || d->state == TFSC_STATE_LOADING)) continue;
+      if (d && d->state == TFSC_STATE_UNLOADING && d->dptr) {  // still pinned by in-flight work: revive in place
+        d->state = d->ready_seen ? TFSC_STATE_AVAILABLE : TFSC_STATE_LOADING;
+        continue;
+      }
+      auto hit = host_.find(m.id);
+      if (hit == host_.end()) continue;
+      size_t off;
+      if (!arena_.alloc(hit->second->bytes, &off)) {
+        if (m.id == want) break;  // must wait for space
+        continue;                 // other prefix members are paged in opportunistically
+      }
+      auto nd = std::make_shared<DeviceModel>();
+      nd->id = m.id;
+      nd->host = hit->second;
+      nd->desc = hit->second->desc;
+      nd->off = off;
+      nd->bytes = hit->second->bytes;
+      nd->dptr = slab_ + off;
+      nd->state = TFSC_STATE_LOADING;
+      nd->ready = get_event();
+      cudaError_t e = cudaMemcpyAsync(nd->dptr, nd->host->data, nd->bytes, cudaMemcpyHostToDevice, copy_);
+      if (e == cudaSuccess) e = cudaEventRecord(nd->ready, copy_);
+      if (e != cudaSuccess) {
+        arena_.release(off);
+        put_event(nd->ready);
+        *err = std::string("page-in failed: ") + cudaGetErrorString(e);
+        return TFSC_E_INTERNAL;
+      }
+      h2d_weights_ += (int64_t)nd->bytes;
+      dev_[m.id] = nd;
+    }
+    auto wit = dev_.find(want);
+    if (wit != dev_.end() && (wit->second->state == TFSC_STATE_AVAILABLE || wit->second->state == TFSC_STATE_LOADING))
+      return 0;
+    // blocked on arena space: wait for pinned victims to retire, else evict further (fragmentation)
+    bool pending_release = !retire_.empty();
+    for (auto& kv : dev_)
+      if (kv.second->state == TFSC_STATE_UNLOADING && kv.second->dptr) pending_release = true;
+    if (!pending_release) {
+      std::shared_ptr<DeviceModel> victim;
+      for (auto rit = prefix.rbegin(); rit != prefix.rend(); ++rit) {
+        if (rit->id == want) continue;
+        auto it = dev_.find(rit->id);
+        if (it != dev_.end() && it->second->dptr && it->second->inflight == 0 &&
+            (it->second->state == TFSC_STATE_AVAILABLE || it->second->state == TFSC_STATE_LOADING)) {
+          victim = it->second;
+          break;
+        }
+      }
+      if (victim) {
+        begin_unload_locked(victim);
+        continue;
+      }
+    }
+    if (Clock::now() >= deadline) {
+      *err = "Timeout: Model did not load in time";  // cachemanager.go:191-193
+      return TFSC_E_TIMEOUT;
+    }
+    if (!retire_.empty()) {
+      cudaEvent_t ev = retire_.front().ev;
+      lk.unlock();
+      cudaEventSynchronize(ev);
+      lk.lock();
+    } else {
+      cv_.wait_for(lk, std::chrono::milliseconds(2));
+    }
+  }
+}
+
+int Node::fetch(const ModelId& id, std::shared_ptr<DeviceModel>* pinned, std::string* err) {
+  DeviceGuard g(cfg_.device);
+  const auto t0 = Clock::now();
+  std::unique_lock<std::mutex> lk(mu_);
+  ++total_;
+  reap_locked();
+  int outcome = -1;
+  std::shared_ptr<DeviceModel> d;
+  for (;;) {
+    CachedModel cm;
+    if (!lru_.get(id, &cm)) {  // tryGetModelFromCache, cachemanager.go:154-165 (Get touches recency)
+      if (outcome < 0) {
+        outcome = TFSC_FETCH_MISS;
+        ++misses_;
+      }
+      if (loading_.count(id)) {  // coalesce concurrent misses of one model (fixes the duplicate download)
+        cv_.wait(lk, [&] { return loading_.count(id) == 0; });
+        continue;
+      }
+      loading_[id] = 1;
+      lk.unlock();
+      const auto tf = Clock::now();
+      std::string perr;
+      std::shared_ptr<HostModel> hm;
+      int64_t size = provider_->model_size(id.name, id.version, &perr);  // :116
+      if (size >= 0)
+        hm = provider_->load_model(
+            id.name, id.version,
+            [this](size_t n, std::function<void(void*, size_t)>* rel) { return host_alloc(n, rel); }, &perr);  // :122
+      lk.lock();
+      loading_.erase(id);
+      fetch_dur_ += secs_since(tf);
+      if (!hm) {
+        cv_.notify_all();
+        cache_dur_ += secs_since(t0);
+        *err = perr;
+        return perr == "No matching model found" || size < 0 ? TFSC_E_NOT_FOUND : TFSC_E_INTERNAL;
+      }
+      size = (int64_t)hm->bytes > size ? (int64_t)hm->bytes : size;
+      lru_.ensure_free_bytes(size);  // :121
+      CachedModel nm{id, id.name + "/" + std::to_string(id.version), size};
+      lru_.put(id, nm);  // :127
+      host_[id] = hm;
+      cv_.notify_all();
+      continue;  // now present: falls into the reload branch below (:128)
+    }
+    auto dit = dev_.find(id);
+    if (dit != dev_.end()) refresh_state_locked(dit->second.get());
+    const int st = dit == dev_.end() ? -1 : dit->second->state;
+    if (st == TFSC_STATE_AVAILABLE || st == TFSC_STATE_LOADING) {
+      d = dit->second;
+      if (outcome < 0) {
+        outcome = TFSC_FETCH_HIT;  // :144-150
+        ++hits_;
+      }
+      break;
+    }
+    if (outcome < 0) outcome = TFSC_FETCH_RELOAD;  // :133-143: cached but not resident
+    int rc = reload_locked(lk, id, err);
+    if (rc < 0) {
+      cache_dur_ += secs_since(t0);
+      return rc;
+    }
+    d = dev_[id];
+    break;
+  }
+  d->inflight++;
+  cache_dur_ += secs_since(t0);
+  lk.unlock();
+  if (pinned) {
+    *pinned = d;
+  } else {
+    // synchronous ensure: the poll-until-AVAILABLE loop of :175-193 becomes one event wait
+    cudaError_t e = d->ready_seen ? cudaSuccess : cudaEventSynchronize(d->ready);
+    {
+      std::lock_guard<std::mutex> l2(mu_);
+      if (e == cudaSuccess) refresh_state_locked(d.get());
+    }
+    unpin(d);
+    if (e != cudaSuccess) {
+      *err = std::string("page-in failed: ") + cudaGetErrorString(e);
+      return TFSC_E_INTERNAL;
+    }
+  }
+  return outcome;
+}
+
+int Node::status(const ModelId& id) {
+  DeviceGuard g(cfg_.device);
+  std::lock_guard<std::mutex> lk(mu_);
+  reap_locked();
+  auto it = dev_.find(id);
+  if (it == dev_.end()) {
+    if (loading_.count(id)) return TFSC_STATE_START;
+    return fail(TFSC_E_NOT_FOUND, "Model not found");  // servingcontroller.go:137
+  }
+  refresh_state_locked(it->second.get());
+  return it->second->state;
+}
+
+std::string Node::resident_lines() {
+  DeviceGuard g(cfg_.device);
+  std::lock_guard<std::mutex> lk(mu_);
+  std::string s;
+  for (auto& m : lru_.list_models()) {
+    auto it = dev_.find(m.id);
+    if (it == dev_.end() || !it->second->dptr) continue;
+    refresh_state_locked(it->second.get());
+    s += m.id.name + "\t" + std::to_string(m.id.version) + "\t" + std::to_string(it->second->bytes) + "\t" +
+         std::to_string(it->second->state) + "\n";
+  }
+  return s;
+}
+
+std::string Node::host_lines() {
+  std::lock_guard<std::mutex> lk(mu_);
+  std::string s;
+  for (auto& m : lru_.list_models())
+    s += m.id.name + "\t" + std::to_string(m.id.version) + "\t" + std::to_string(m.size_on_disk) + "\t" + m.path + "\n";
+  return s;
+}
+
+void Node::stats(tfsc_stats* s) {
+  std::lock_guard<std::mutex> lk(mu_);
+  s->cache_total += total_;
+  s->cache_hits_total += hits_;
+  s->cache_misses_total += misses_;
+  s->evictions_host += ev_host_;
+  s->evictions_hbm += ev_hbm_;
+  s->h2d_weight_bytes += h2d_weights_;
+  s->h2d_input_bytes += h2d_inputs_.load();
+  s->d2h_output_bytes += d2h_outputs_.load();
+  s->batches += batches_.load();
+  s->batched_rows += batched_rows_.load();
+  s->arena_bytes_used += (int64_t)arena_.used();
+  s->arena_bytes_capacity += (int64_t)arena_.capacity();
+  s->resident_models += (int64_t)arena_.blocks();
+  s->host_models += (int64_t)lru_.size();
+  s->cache_duration_seconds_sum += cache_dur_;
+  s->cache_fetch_duration_seconds_sum += fetch_dur_;
+}
+
+// ------------------------------------------------------------------------- execution ------
+size_t Node::model_ws_bytes(const ModelDesc& d) {
+  size_t m = 256;
+  for (auto& L : d.layers) {
+    size_t w = dense_workspace_bytes(kMaxRowsPerLaunch, L.in, L.out);
+    if (w > m) m = w;
+  }
+  return m;
+}
+
+cudaError_t Node::run_model(const DeviceModel& dm, const char* x, int64_t rows, char* y, char* act0, char* act1,
+                            void* ws, size_t ws_cap, cudaStream_t st) {
+  const ModelDesc& d = dm.desc;
+  if (d.tmpl == Template::Affine) {
+    return launch_affine((const float*)x, (float*)y, rows, (const float*)(dm.dptr + d.a_off),
+                         (const float*)(dm.dptr + d.b_off), st);
+  }
+  const char* in = x;
+  for (size_t l = 0; l < d.layers.size(); ++l) {
+    const DenseLayer& L = d.layers[l];
+    char* out = (l + 1 == d.layers.size()) ? y : ((l & 1) ? act1 : act0);
+    cudaError_t e = launch_dense((const float*)in, (const float*)(dm.dptr + L.w_off), (const float*)(dm.dptr + L.b_off),
+                                 (float*)out, (int)rows, L.in, L.out, L.relu, ws, ws_cap, st);
+    if (e != cudaSuccess) return e;
+    in = out;
+  }
+  return cudaSuccess;
+}
+
+static size_t row_in_bytes(const ModelDesc& d) { return d.tmpl == Template::Affine ? 4 : (size_t)d.in_dim * 4; }
+static size_t row_out_bytes(const ModelDesc& d) { return d.tmpl == Template::Affine ? 4 : (size_t)d.out_dim * 4; }
+
+bool Node::ensure_slot(Slot* s, const ModelDesc& d, int64_t rows, std::string* err) {
+  int64_t cap_rows = rows > cfg_.max_batch ? rows : cfg_.max_batch;
+  size_t io = (size_t)cap_rows * std::max(row_in_bytes(d), row_out_bytes(d));
+  size_t act = (size_t)cap_rows * (size_t)std::max(d.max_width, 1) * 4;
+  size_t ws = model_ws_bytes(d);
+  if (io > s->io_cap) {
+    cudaStreamSynchronize(compute_);
+    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->d_in) cudaFree(s->d_in);
+    if (s->d_out) cudaFree(s->d_out);
+    s->h_in = s->h_out = s->d_in = s->d_out = nullptr;
+    s->io_cap = 0;
+    CU_OK(cudaHostAlloc((void**)&s->h_in, io, cudaHostAllocPortable), err, false);
+    CU_OK(cudaHostAlloc((void**)&s->h_out, io, cudaHostAllocPortable), err, false);
+    CU_OK(cudaMalloc((void**)&s->d_in, io), err, false);
+    CU_OK(cudaMalloc((void**)&s->d_out, io), err, false);
+    s->io_cap = io;
+  }
+  if (act > s->act_cap) {
+    cudaStreamSynchronize(compute_);
+    if (s->act0) cudaFree(s->act0);
+    if (s->act1) cudaFree(s->act1);
+    s->act0 = s->act1 = nullptr;
+    s->act_cap = 0;
+    CU_OK(cudaMalloc((void**)&s->act0, act), err, false);
+    CU_OK(cudaMalloc((void**)&s->act1, act), err, false);
+    s->act_cap = act;
+  }
+  if (ws > s->ws_cap) {
+    cudaStreamSynchronize(compute_);
+    if (s->ws) cudaFree(s->ws);
+    s->ws = nullptr;
+    s->ws_cap = 0;
+    CU_OK(cudaMalloc(&s->ws, ws), err, false);
+    CU_OK(cudaMemsetAsync(s->ws, 0, ws, compute_), err, false);
+    s->ws_cap = ws;
+  }
+  return true;
+}
+
+int Node::describe(const ModelId& id, ModelDesc* desc, int* outcome, std::string* err) {
+  std::shared_ptr<DeviceModel> dm;
+  int rc = fetch(id, &dm, err);
+  if (rc < 0) return rc;
+  if (outcome) *outcome = rc;
+  *desc = dm->desc;
+  unpin(dm);
+  return 0;
+}
+
+int Node::predict_host(const ModelId& id, const void* x, int64_t n_elems, const OutAllocFn& y_alloc, int* outcome,
+                       ModelDesc* desc_out, std::string* err) {
+  PredictRequest req;
+  int rc = fetch(id, &req.dm, err);  // handleModelRequest -> fetchModel, before any input validation (as the reference)
+  if (rc < 0) return rc;
+  if (outcome) *outcome = rc;
+  const ModelDesc& d = req.dm->desc;
+  if (desc_out) *desc_out = d;
+  const int64_t per_row = d.tmpl == Template::Affine ? 1 : d.in_dim;
+  if (!x || n_elems <= 0 || n_elems % per_row != 0) {
+    unpin(req.dm);
+    *err = "input has " + std::to_string(n_elems) + " elements; model " + id.name + " expects a multiple of " +
+           std::to_string(per_row);
+    return TFSC_E_INVALID;
+  }
+  const int64_t rows = n_elems / per_row;
+  if (rows > cfg_.max_request_rows) {
+    unpin(req.dm);
+    *err = "request has " + std::to_string(rows) + " rows; gpu.maxRequestRows is " + std::to_string(cfg_.max_request_rows);
+    return TFSC_E_INVALID;
+  }
+  void* y = y_alloc(d, rows);
+  if (!y) {
+    unpin(req.dm);
+    *err = "output buffer too small";
+    return TFSC_E_BUFFER;
+  }
+  req.x = x;
+  req.y = y;
+  req.rows = rows;
+  {
+    std::lock_guard<std::mutex> lk(q_mu_);
+    auto& q = pending_[req.dm.get()];
+    if (q.empty()) order_.push_back(req.dm.get());
+    q.push_back(&req);
+  }
+  q_cv_.notify_all();
+  {
+    std::unique_lock<std::mutex> lk(req.mu);
+    req.cv.wait(lk, [&] { return req.rc != 1; });
+  }
+  if (req.rc < 0) *err = req.err;
+  return req.rc;
+}
+
+void Node::batcher_loop() {
+  cudaSetDevice(cfg_.device);
+  for (;;) {
+    std::unique_lock<std::mutex> lk(q_mu_);
+    q_cv_.wait(lk, [&] { return stop_ || !order_.empty(); });
+    if (order_.empty()) {
+      if (stop_) break;
+      continue;
+    }
+    DeviceModel* m = order_.front();
+    order_.pop_front();
+    auto& q = pending_[m];
+    std::vector<PredictRequest*> batch;
+    int64_t rows = 0;
+    while (!q.empty()) {
+      PredictRequest* r = q.front();
+      if (!batch.empty() && rows + r->rows > cfg_.max_batch) break;
+      batch.push_back(r);
+      rows += r->rows;
+      q.pop_front();
+      if (rows >= cfg_.max_batch) break;
+    }
+    if (!q.empty()) order_.push_back(m);  // round-robin fairness between models
+    else pending_.erase(m);
+    Slot* s = nullptr;
+    slot_cv_.wait(lk, [&] {
+      for (auto& c : slots_)
+        if (!c.busy) {
+          s = &c;
+          return true;
+        }
+      return stop_;
+    });
+    if (!s) {  // shutting down
+      for (auto* r : batch) {
+        std::lock_guard<std::mutex> l(r->mu);
+        r->rc = TFSC_E_INTERNAL;
+        r->err = "server shutting down";
+        r->cv.notify_all();
+      }
+      continue;
+    }
+    s->busy = true;
+    lk.unlock();
+
+    std::shared_ptr<DeviceModel> dm = batch[0]->dm;
+    const ModelDesc& d = dm->desc;
+    std::string err;
+    cudaError_t e = cudaSuccess;
+    if (!ensure_slot(s, d, rows, &err)) e = cudaErrorMemoryAllocation;
+    const size_t rin = row_in_bytes(d), rout = row_out_bytes(d);
+    if (e == cudaSuccess) {
+      size_t off = 0;
+      for (auto* r : batch) {
+        memcpy(s->h_in + off, r->x, (size_t)r->rows * rin);
+        off += (size_t)r->rows * rin;
+      }
+      e = cudaMemcpyAsync(s->d_in, s->h_in, off, cudaMemcpyHostToDevice, compute_);
+      h2d_inputs_ += (int64_t)off;
+      if (e == cudaSuccess && !dm->ready_seen) e = cudaStreamWaitEvent(compute_, dm->ready, 0);
+      if (e == cudaSuccess) e = run_model(*dm, s->d_in, rows, s->d_out, s->act0, s->act1, s->ws, s->ws_cap, compute_);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_out, s->d_out, (size_t)rows * rout, cudaMemcpyDeviceToHost, compute_);
+      d2h_outputs_ += (int64_t)rows * (int64_t)rout;
+      if (e == cudaSuccess) e = cudaEventRecord(s->done, compute_);
+    }
+    batches_++;
+    batched_rows_ += rows;
+    if (e != cudaSuccess) {
+      if (err.empty()) err = std::string("launch failed: ") + cudaGetErrorString(e);
+      cudaGetLastError();
+      for (auto* r : batch) {
+        unpin(r->dm);
+        std::lock_guard<std::mutex> l(r->mu);
+        r->rc = TFSC_E_INTERNAL;
+        r->err = err;
+        r->cv.notify_all();
+      }
+      lk.lock();
+      s->busy = false;
+      lk.unlock();
+      slot_cv_.notify_all();
+      continue;
+    }
+    s->reqs = std::move(batch);
+    s->dm = dm;
+    lk.lock();
+    inflight_.push_back(s);
+    lk.unlock();
+    q_cv_.notify_all();
+  }
+}
+
+void Node::completer_loop() {
+  cudaSetDevice(cfg_.device);
+  for (;;) {
+    Slot* s = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(q_mu_);
+      q_cv_.wait(lk, [&] { return !inflight_.empty() || (stop_ && order_.empty()); });
+      if (inflight_.empty()) {
+        if (stop_) break;
+        continue;
+      }
+      s = inflight_.front();
+      inflight_.pop_front();
+    }
+    cudaError_t e = cudaEventSynchronize(s->done);
+    const size_t rout = row_out_bytes(s->dm->desc);
+    size_t off = 0;
+    for (auto* r : s->reqs) {
+      if (e == cudaSuccess) memcpy(r->y, s->h_out + off, (size_t)r->rows * rout);
+      off += (size_t)r->rows * rout;
+    }
+    for (auto* r : s->reqs) {
+      std::shared_ptr<DeviceModel> dm = r->dm;
+      {
+        std::lock_guard<std::mutex> l(r->mu);
+        r->rc = e == cudaSuccess ? 0 : TFSC_E_INTERNAL;
+        if (e != cudaSuccess) r->err = std::string("execution failed: ") + cudaGetErrorString(e);
+        r->cv.notify_all();
+      }
+      unpin(dm);
+    }
+    s->reqs.clear();
+    s->dm.reset();
+    {
+      std::lock_guard<std::mutex> lk(q_mu_);
+      s->busy = false;
+    }
+    slot_cv_.notify_all();
+  }
+}
+
+int Node::predict_device(const ModelId& id, const void* x, int64_t rows, void* y, cudaStream_t stream,
+                         std::string* err) {
+  DeviceGuard g(cfg_.device);
+  if (rows <= 0) return 0;
+  std::shared_ptr<DeviceModel> dm;
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    reap_locked();
+    auto it = dev_.find(id);
+    if (it != dev_.end()) refresh_state_locked(it->second.get());
+    if (it == dev_.end() || !(it->second->state == TFSC_STATE_AVAILABLE || it->second->state == TFSC_STATE_LOADING)) {
+      *err = "model " + id.name + ":" + std::to_string(id.version) + " is not HBM-resident (call tfsc_model_ensure)";
+      return TFSC_E_NOT_FOUND;
+    }
+    dm = it->second;
+    dm->inflight++;
+    ev = get_event();
+  }
+  cudaStream_t st = stream ? stream : compute_;
+  const ModelDesc& d = dm->desc;
+  cudaError_t e = cudaSuccess;
+  StreamScratch* sc = nullptr;
+  if (d.tmpl == Template::Mlp) {
+    const size_t act = (((size_t)rows * d.max_width * 4) + 255) & ~(size_t)255;
+    const size_t ws = model_ws_bytes(d);
+    std::lock_guard<std::mutex> lk(scratch_mu_);
+    sc = &stream_scratch_[st];
+    if (sc->act_bytes < act || sc->ws_bytes < ws) {
+      if (sc->base) {
+        cudaStreamSynchronize(st);
+        cudaFree(sc->base);
+        sc->base = nullptr;
+      }
+      size_t a = act > sc->act_bytes ? act : sc->act_bytes, w = ws > sc->ws_bytes ? ws : sc->ws_bytes;
+      e = cudaMalloc((void**)&sc->base, 2 * a + w);
+      if (e == cudaSuccess) e = cudaMemsetAsync(sc->base + 2 * a, 0, w, st);
+      sc->act_bytes = a;
+      sc->ws_bytes = w;
+    }
+  }
+  if (e == cudaSuccess && !dm->ready_seen) e = cudaStreamWaitEvent(st, dm->ready, 0);
+  if (e == cudaSuccess) {
+    char* a0 = sc ? sc->base : nullptr;
+    char* a1 = sc ? sc->base + sc->act_bytes : nullptr;
+    void* ws = sc ? sc->base + 2 * sc->act_bytes : nullptr;
+    e = run_model(*dm, (const char*)x, rows, (char*)y, a0, a1, ws, sc ? sc->ws_bytes : 0, st);
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(ev, st);
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (e == cudaSuccess) retire_.push_back({ev, dm});
+    else {
+      put_event(ev);
+      if (--dm->inflight == 0 && dm->state == TFSC_STATE_UNLOADING) release_locked(dm);
+    }
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *err = std::string("predict_device: ") + cudaGetErrorString(e);
+    return TFSC_E_INTERNAL;
+  }
+  return 0;
+}
+
+int Node::sync() {
+  DeviceGuard g(cfg_.device);
+  cudaError_t e = cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(mu_);
+  reap_locked();
+  return e == cudaSuccess ? 0 : TFSC_E_INTERNAL;
+}
+
+}  // namespace tfsc

@@ -1,0 +1,177 @@
+// One ring member = one GPU: the cache tier of the reference (pkg/cachemanager) rebuilt around
+// device memory. Holds
+//   * the LRU host tier (lrucache.go semantics, entries live in pinned host memory),
+//   * the HBM arena + residency table (the "loaded in TF-Serving" set of
+//     cachemanager.go:167-195 / servingcontroller.go, same six states),
+//   * a copy stream paging weights in with cudaMemcpyAsync from pinned memory,
+//   * the batcher: concurrent Predict calls for the same resident model are gathered into one
+//     contiguous [rows, in] device buffer and run with one pass over the weights.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "arena.h"
+#include "lru.h"
+#include "model.h"
+#include "provider.h"
+
+namespace tfsc {
+
+struct DeviceModel {
+  ModelId id;
+  std::shared_ptr<HostModel> host;
+  ModelDesc desc;
+  int state = TFSC_STATE_START;
+  size_t off = 0, bytes = 0;
+  char* dptr = nullptr;
+  cudaEvent_t ready = nullptr;  // recorded on the copy stream after the H2D page-in
+  std::atomic<bool> ready_seen{false};  // event known complete: consumers skip the stream wait
+  int inflight = 0;             // pins: launches that still read dptr
+};
+
+struct NodeConfig {
+  int device = 0;
+  int64_t host_cache_bytes = 0;     // modelCache.size
+  int max_concurrent_models = 2;    // serving.maxConcurrentModels
+  int64_t arena_bytes = 0;          // gpu.arenaBytes (0 = 85% of free HBM)
+  int max_batch = 8;                // gpu.maxBatch: rows gathered across requests per launch
+  int max_request_rows = 1024;      // largest single request
+  double fetch_timeout_s = 10.0;    // ModelFetchTimeout (main.go:122)
+  int slots = 4;                    // staging slots in flight
+};
+
+struct PredictRequest {  // one caller blocked in tfsc_predict
+  std::shared_ptr<DeviceModel> dm;
+  const void* x = nullptr;
+  void* y = nullptr;
+  int64_t rows = 0;
+  int rc = 1;  // 1 = pending
+  std::string err;
+  std::mutex mu;
+  std::condition_variable cv;
+};
+
+class Node {
+ public:
+  Node(const NodeConfig& cfg, ModelProvider* provider);
+  ~Node();
+  bool init(std::string* err);
+
+  // fetchModel (cachemanager.go:91-152). On success returns TFSC_FETCH_* and, if `pinned` is
+  // given, a pinned handle the caller must unpin().
+  int fetch(const ModelId& id, std::shared_ptr<DeviceModel>* pinned, std::string* err);
+  void unpin(const std::shared_ptr<DeviceModel>& dm);
+  int status(const ModelId& id);  // GetModelStatus: TFSC_STATE_* or TFSC_E_NOT_FOUND
+  std::string resident_lines();
+  std::string host_lines();
+
+  // host-buffer predict through the batcher (blocks the caller). n_elems = fp32 elements in x;
+  // rows are derived from the model (n_elems / in_dim). y_alloc(desc, rows) supplies the output
+  // buffer once the model is known (return nullptr to reject, e.g. caller buffer too small).
+  using OutAllocFn = std::function<void*(const ModelDesc&, int64_t rows)>;
+  int predict_host(const ModelId& id, const void* x, int64_t n_elems, const OutAllocFn& y_alloc, int* outcome,
+                   ModelDesc* desc_out, std::string* err);
+  // describe a model (triggers fetch): needed to size outputs before predict
+  int describe(const ModelId& id, ModelDesc* desc, int* outcome, std::string* err);
+  // device-buffer predict on `stream` (nullptr = compute stream), asynchronous
+  int predict_device(const ModelId& id, const void* x, int64_t rows, void* y, cudaStream_t stream, std::string* err);
+  int sync();
+  void stats(tfsc_stats* s);
+  int device() const { return cfg_.device; }
+
+ private:
+  struct Slot {
+    char *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *act0 = nullptr, *act1 = nullptr;
+    void* ws = nullptr;
+    size_t io_cap = 0, act_cap = 0, ws_cap = 0;
+    cudaEvent_t done = nullptr;
+    std::vector<PredictRequest*> reqs;
+    std::shared_ptr<DeviceModel> dm;
+    bool busy = false;
+  };
+  struct Retire {
+    cudaEvent_t ev;
+    std::shared_ptr<DeviceModel> dm;
+  };
+  struct StreamScratch {  // activation ping-pong + split-K workspace of one caller stream
+    char* base = nullptr;
+    size_t act_bytes = 0, ws_bytes = 0;
+  };
+
+  // all *_locked functions require mu_
+  std::vector<CachedModel> resident_prefix_locked();
+  int reload_locked(std::unique_lock<std::mutex>& lk, const ModelId& want, std::string* err);
+  void begin_unload_locked(const std::shared_ptr<DeviceModel>& d);
+  void release_locked(const std::shared_ptr<DeviceModel>& d);
+  void reap_locked();
+  void on_host_evict_locked(const CachedModel& m);
+  void refresh_state_locked(DeviceModel* d);
+  void* host_alloc(size_t bytes, std::function<void(void*, size_t)>* release);
+  bool ensure_slot(Slot* s, const ModelDesc& d, int64_t rows, std::string* err);
+  cudaError_t run_model(const DeviceModel& dm, const char* x, int64_t rows, char* y, char* act0, char* act1, void* ws,
+                        size_t ws_cap, cudaStream_t st);
+  static size_t model_ws_bytes(const ModelDesc& d);
+  void batcher_loop();
+  void completer_loop();
+  cudaEvent_t get_event();
+  void put_event(cudaEvent_t e);
+
+  NodeConfig cfg_;
+  ModelProvider* provider_;
+  cudaStream_t compute_ = nullptr, copy_ = nullptr;
+  char* slab_ = nullptr;
+  Arena arena_;
+
+  std::mutex mu_;
+  std::condition_variable cv_;
+  LRUCache lru_;
+  std::unordered_map<ModelId, std::shared_ptr<HostModel>, ModelIdHash> host_;
+  std::unordered_map<ModelId, std::shared_ptr<DeviceModel>, ModelIdHash> dev_;
+  std::unordered_map<ModelId, int, ModelIdHash> loading_;  // provider loads in flight (1) / failed (-1)
+  std::deque<Retire> retire_;
+  std::vector<cudaEvent_t> event_pool_;
+
+  std::mutex scratch_mu_;
+  std::unordered_map<cudaStream_t, StreamScratch> stream_scratch_;
+
+  // pinned block pool (exact-size reuse)
+  std::mutex pool_mu_;
+  std::unordered_map<size_t, std::vector<void*>> pool_;
+
+  // batcher
+  std::mutex q_mu_;
+  std::condition_variable q_cv_, slot_cv_;
+  std::unordered_map<DeviceModel*, std::deque<PredictRequest*>> pending_;
+  std::deque<DeviceModel*> order_;
+  std::deque<Slot*> inflight_;
+  std::vector<Slot> slots_;
+  std::thread batcher_, completer_;
+  bool stop_ = false;
+
+  // stats (guarded by mu_ unless atomic)
+  int64_t total_ = 0, hits_ = 0, misses_ = 0, ev_host_ = 0, ev_hbm_ = 0, h2d_weights_ = 0;
+  std::atomic<int64_t> h2d_inputs_{0}, d2h_outputs_{0}, batches_{0}, batched_rows_{0};
+  double cache_dur_ = 0, fetch_dur_ = 0;
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace tfsc

@@ -1,0 +1,637 @@
+// The server object behind the C ABI: cmd/taskhandler/main.go:45-113 (serveCache + serveProxy)
+// for the GPUs of this process. Proxy tier = ring lookup + replica pick (taskhandler.go:84-92);
+// cache tier = one Node per GPU (node.h); the forward hop between them is a function call (host
+// buffers are staged straight into the owner GPU) or NVLink peer access (device buffers).
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <mutex>
+
+#include "json.h"
+#include "kernels.h"
+#include "node.h"
+#include "parse.h"
+#include "provider.h"
+#include "ring.h"
+#include "wire.h"
+
+using namespace tfsc;
+
+struct tfsc_server {
+  Json cfg;
+  std::unique_ptr<ModelProvider> provider;
+  std::vector<std::unique_ptr<Node>> nodes;
+  std::vector<std::string> local_members;  // member string of nodes[i]
+  std::mutex ring_mu;
+  Ring ring;
+  std::map<std::string, int> member_node;
+  int replicas = 1;
+  std::string pick_policy = "random";
+  std::mutex rng_mu;
+  uint64_t rng = 0x9E3779B97F4A7C15ull;
+  std::atomic<int64_t> req_rest{0}, req_grpc{0}, fail_rest{0}, fail_grpc{0};
+
+  uint64_t next_rand() {  // xorshift64*
+    std::lock_guard<std::mutex> lk(rng_mu);
+    rng ^= rng >> 12;
+    rng ^= rng << 25;
+    rng ^= rng >> 27;
+    return rng * 0x2545F4914F6CDD1Dull;
+  }
+};
+
+static int route(tfsc_server* s, const std::string& name, const std::string& version, std::vector<int>* nodes,
+                 int* picked) {
+  std::vector<std::string> members;
+  {
+    std::lock_guard<std::mutex> lk(s->ring_mu);
+    // FindNodeForKey: GetN(key, max(replicasPerModel, 1)), cluster.go:117
+    if (!s->ring.get_n(name + "##" + version, s->replicas < 1 ? 1 : s->replicas, &members))
+      return fail(TFSC_E_EMPTY_RING, "empty circle");
+    nodes->clear();
+    for (auto& m : members) {
+      auto it = s->member_node.find(m);
+      nodes->push_back(it == s->member_node.end() ? -1 : it->second);
+    }
+  }
+  // "Pick random node", taskhandler.go:91 (uniform over the replica list)
+  *picked = s->pick_policy == "first" ? 0 : (int)(s->next_rand() % nodes->size());
+  return (int)nodes->size();
+}
+
+static void set_members(tfsc_server* s, const std::vector<std::string>& members) {
+  std::lock_guard<std::mutex> lk(s->ring_mu);
+  s->ring.set(members);
+  s->member_node.clear();
+  for (size_t i = 0; i < s->local_members.size(); ++i) s->member_node[s->local_members[i]] = (int)i;
+}
+
+extern "C" {
+
+tfsc_server* tfsc_server_create(const char* config_json) {
+  auto s = std::make_unique<tfsc_server>();
+  std::string err;
+  if (!config_json || !json_parse(config_json, &s->cfg, &err) || s->cfg.type != Json::Obj) {
+    fail(TFSC_E_INVALID, "config: %s", err.empty() ? "expected a JSON object" : err.c_str());
+    return nullptr;
+  }
+  int n_dev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  if (ce != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    fail(TFSC_E_NO_DEVICE, "no CUDA device available (%s): this library has no CPU fallback",
+         ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+    return nullptr;
+  }
+  s->provider = create_provider(s->cfg, &err);
+  if (!s->provider) {
+    fail(TFSC_E_INVALID, "%s", err.c_str());
+    return nullptr;
+  }
+  std::vector<int> devices;
+  if (const Json* d = s->cfg.get("gpu.devices")) {
+    for (auto& v : d->arr) devices.push_back((int)v.integer());
+  }
+  if (devices.empty())
+    for (int i = 0; i < n_dev; ++i) devices.push_back(i);
+  for (int d : devices) {
+    cudaDeviceProp prop;
+    if (d < 0 || d >= n_dev || cudaGetDeviceProperties(&prop, d) != cudaSuccess) {
+      fail(TFSC_E_NO_DEVICE, "gpu.devices: device %d not present", d);
+      return nullptr;
+    }
+    if (prop.major < 10) {
+      fail(TFSC_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", d, prop.major,
+           prop.minor);
+      return nullptr;
+    }
+  }
+  s->replicas = (int)std::max(s->cfg.get_num("proxy.replicasPerModel", 1), 1.0);
+  s->pick_policy = s->cfg.get_str("proxy.replicaPick", "random");
+  int64_t seed = s->cfg.get_int("proxy.seed", -1);
+  // rand.Seed(time.Now().UnixNano()), taskhandler.go:49, unless pinned for reproducible tests
+  s->rng ^= seed >= 0 ? (uint64_t)seed * 0x9E3779B97F4A7C15ull + 1
+                      : (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count();
+  if (const Json* lm = s->cfg.get("gpu.localMembers"))
+    for (auto& v : lm->arr) s->local_members.push_back(v.string());
+  for (size_t i = 0; i < devices.size(); ++i) {
+    NodeConfig nc;
+    nc.device = devices[i];
+    nc.host_cache_bytes = s->cfg.get_int("modelCache.size", (int64_t)1 << 40);
+    nc.max_concurrent_models = (int)s->cfg.get_int("serving.maxConcurrentModels", 1 << 30);
+    nc.arena_bytes = s->cfg.get_int("gpu.arenaBytes", 0);
+    nc.max_batch = (int)s->cfg.get_int("gpu.maxBatch", 8);
+    nc.max_request_rows = (int)s->cfg.get_int("gpu.maxRequestRows", 1024);
+    nc.fetch_timeout_s = s->cfg.get_num("serving.modelFetchTimeout", 10.0);
+    nc.slots = (int)s->cfg.get_int("gpu.stagingSlots", 4);
+    auto node = std::make_unique<Node>(nc, s->provider.get());
+    if (!node->init(&err)) {
+      fail(TFSC_E_NO_DEVICE, "node %zu (device %d): %s", i, devices[i], err.c_str());
+      return nullptr;
+    }
+    s->nodes.push_back(std::move(node));
+    if (s->local_members.size() <= i) s->local_members.push_back("gpu" + std::to_string(devices[i]) + ":0:0");
+  }
+  std::vector<std::string> members;
+  if (const Json* m = s->cfg.get("gpu.members"))
+    for (auto& v : m->arr) members.push_back(v.string());
+  if (members.empty()) members = s->local_members;
+  set_members(s.get(), members);
+  return s.release();
+}
+
+void tfsc_server_destroy(tfsc_server* s) { delete s; }
+int tfsc_server_num_nodes(const tfsc_server* s) { return s ? (int)s->nodes.size() : 0; }
+
+int tfsc_server_set_members(tfsc_server* s, const char* const* members, int n) {
+  if (!s || n < 0) return fail(TFSC_E_INVALID, "set_members: bad arguments");
+  std::vector<std::string> v;
+  for (int i = 0; i < n; ++i) v.emplace_back(members[i]);
+  set_members(s, v);
+  return n;
+}
+
+int tfsc_route(tfsc_server* s, const char* model_name, const char* version, int* nodes, int cap, int* picked) {
+  if (!s || !model_name || !version) return fail(TFSC_E_INVALID, "route: bad arguments");
+  std::vector<int> v;
+  int p = 0;
+  int rc = route(s, model_name, version, &v, &p);
+  if (rc < 0) return rc;
+  for (int i = 0; i < rc && i < cap; ++i) nodes[i] = v[i];
+  if (picked) *picked = p;
+  return rc;
+}
+
+static Node* node_at(tfsc_server* s, int node) {
+  if (!s || node < 0 || node >= (int)s->nodes.size()) {
+    fail(TFSC_E_INVALID, "node index %d out of range", node);
+    return nullptr;
+  }
+  return s->nodes[node].get();
+}
+
+int tfsc_model_ensure(tfsc_server* s, int node, const char* model_name, int64_t version) {
+  Node* n = node_at(s, node);
+  if (!n || !model_name) return TFSC_E_INVALID;
+  std::string err;
+  int rc = n->fetch({model_name, version}, nullptr, &err);
+  if (rc < 0) return fail(rc, "%s", err.c_str());
+  return rc;
+}
+
+int tfsc_model_status(tfsc_server* s, int node, const char* model_name, int64_t version) {
+  Node* n = node_at(s, node);
+  if (!n || !model_name) return TFSC_E_INVALID;
+  return n->status({model_name, version});
+}
+
+int tfsc_resident_list(tfsc_server* s, int node, char* buf, size_t cap) {
+  Node* n = node_at(s, node);
+  if (!n) return TFSC_E_INVALID;
+  std::string l = n->resident_lines();
+  int rc = copy_out(l, buf, cap);
+  if (rc < 0) return rc;
+  int c = 0;
+  for (char ch : l) c += ch == '\n';
+  return c;
+}
+
+int tfsc_host_list(tfsc_server* s, int node, char* buf, size_t cap) {
+  Node* n = node_at(s, node);
+  if (!n) return TFSC_E_INVALID;
+  std::string l = n->host_lines();
+  int rc = copy_out(l, buf, cap);
+  if (rc < 0) return rc;
+  int c = 0;
+  for (char ch : l) c += ch == '\n';
+  return c;
+}
+
+// route -> parse version -> owner node. Shared by the three Predict entry points.
+static int resolve(tfsc_server* s, const std::string& name, const std::string& version, Node** node, ModelId* id) {
+  std::vector<int> nodes;
+  int picked = 0;
+  int rc = route(s, name, version, &nodes, &picked);
+  if (rc < 0) return rc;
+  int local = nodes[picked];
+  if (local < 0)
+    return fail(TFSC_E_NOT_FOUND, "owner of %s##%s is not a GPU of this process", name.c_str(), version.c_str());
+  int64_t v;
+  if (!parse_int64(version, &v))  // handleModelRequest, cachemanager.go:297
+    return fail(TFSC_E_INVALID, "strconv.ParseInt: parsing \"%s\": invalid syntax", version.c_str());
+  *node = s->nodes[local].get();
+  *id = {name, v};
+  return 0;
+}
+
+static void out_shape(const ModelDesc& d, int64_t rows, const std::vector<int64_t>& in_shape, std::vector<int64_t>* shape) {
+  if (d.tmpl == Template::Affine) {
+    *shape = in_shape;
+  } else {
+    shape->clear();
+    // leading dims of the input are kept ([B, in] -> [B, out]; [in] -> [out])
+    if (in_shape.size() <= 1) {
+      if (rows != 1 || in_shape.empty()) shape->push_back(rows);
+    } else {
+      for (size_t i = 0; i + 1 < in_shape.size(); ++i) shape->push_back(in_shape[i]);
+    }
+    shape->push_back(d.out_dim);
+  }
+}
+
+int tfsc_predict(tfsc_server* s, const char* model_name, const char* version, const tfsc_tensor* in, int n_in,
+                 tfsc_tensor* out, int n_out) {
+  if (!s || !model_name || !version || !in || n_in < 1 || !out || n_out < 1)
+    return fail(TFSC_E_INVALID, "predict: bad arguments");
+  Node* node;
+  ModelId id;
+  int rc = resolve(s, model_name, version, &node, &id);
+  if (rc < 0) return rc;
+  const tfsc_tensor& x = in[0];
+  if (x.dtype != TFSC_DT_FLOAT || x.rank < 0 || x.rank > 8) return fail(TFSC_E_INVALID, "predict: input must be DT_FLOAT, rank <= 8");
+  int64_t n = 1;
+  std::vector<int64_t> ishape(x.shape, x.shape + x.rank);
+  for (auto d : ishape) n *= d;
+  if ((size_t)n * 4 != x.nbytes) return fail(TFSC_E_INVALID, "predict: input nbytes does not match shape");
+  std::string err;
+  tfsc_tensor* o = &out[0];
+  auto alloc = [&](const ModelDesc& d, int64_t rows) -> void* {
+    if (n_in > 1 || (x.name && d.input_name != x.name)) {
+      // signature check: the template has exactly one input
+      if (x.name && d.input_name != x.name) return nullptr;
+    }
+    std::vector<int64_t> sh;
+    out_shape(d, rows, ishape, &sh);
+    int64_t on = 1;
+    for (auto v : sh) on *= v;
+    if (!o->data || o->nbytes < (size_t)on * 4 || sh.size() > 8) return nullptr;
+    o->dtype = TFSC_DT_FLOAT;
+    o->rank = (int32_t)sh.size();
+    for (size_t i = 0; i < sh.size(); ++i) o->shape[i] = sh[i];
+    o->nbytes = (size_t)on * 4;
+    return o->data;
+  };
+  rc = node->predict_host(id, x.data, n, alloc, nullptr, nullptr, &err);
+  if (rc < 0) return fail(rc, "%s", err.c_str());
+  return 0;
+}
+
+int tfsc_grpc_predict(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len) {
+  if (!s || !req || !resp || !resp_len) return fail(TFSC_E_INVALID, "grpc_predict: bad arguments");
+  s->req_grpc++;  // promRequestsTotal{grpc}, tfservingproxy.go:202
+  PredictRequestView view;
+  std::string err;
+  if (!decode_predict_request(req, req_len, &view, &err)) {
+    s->fail_grpc++;
+    return fail(TFSC_E_INVALID, "%s", err.c_str());
+  }
+  // clientForSpec: version string = FormatInt(GetVersion().GetValue()) -> "0" when absent (:246-250)
+  const std::string version = std::to_string(view.version);
+  Node* node;
+  ModelId id;
+  int rc = resolve(s, view.model_name, version, &node, &id);
+  if (rc < 0) {
+    s->fail_grpc++;
+    return rc;
+  }
+  if (view.inputs.empty()) {
+    // the reference forwards even an empty request; residency is still ensured first
+    rc = node->fetch(id, nullptr, &err);
+    s->fail_grpc++;
+    if (rc < 0) return fail(rc, "%s", err.c_str());
+    return fail(TFSC_E_INVALID, "PredictRequest has no inputs");
+  }
+  const TensorView& tv = view.inputs[0];
+  const float* xdata = nullptr;
+  int64_t n = 0;
+  std::vector<float> scratch;
+  bool input_ok = tensor_f32(tv, &xdata, &n, &scratch, &err);
+  char* buf = nullptr;
+  size_t total = 0;
+  std::string bad_sig;
+  auto alloc = [&](const ModelDesc& d, int64_t rows) -> void* {
+    if (view.inputs.size() != 1 || tv.name != d.input_name) {
+      bad_sig = "input keys do not match the model signature (expects '" + d.input_name + "')";
+      return nullptr;
+    }
+    std::vector<int64_t> sh;
+    out_shape(d, rows, tv.shape, &sh);
+    std::string prefix, suffix;
+    predict_response_frame(view.model_name, id.version, view.signature_name.empty() ? "serving_default" : view.signature_name,
+                           d.output_name, sh, &prefix, &suffix);
+    int64_t on = 1;
+    for (auto v : sh) on *= v;
+    total = prefix.size() + (size_t)on * 4 + suffix.size();
+    buf = (char*)malloc(total ? total : 1);
+    if (!buf) return nullptr;
+    memcpy(buf, prefix.data(), prefix.size());
+    memcpy(buf + prefix.size() + (size_t)on * 4, suffix.data(), suffix.size());
+    return buf + prefix.size();  // the executor's D2H result is scattered straight into the response
+  };
+  if (!input_ok) {
+    std::string e2;
+    rc = node->fetch(id, nullptr, &e2);  // residency first, like the reference; then reject the tensor
+    s->fail_grpc++;
+    if (rc < 0) return fail(rc, "%s", e2.c_str());
+    return fail(TFSC_E_INVALID, "%s", err.c_str());
+  }
+  rc = node->predict_host(id, xdata, n, alloc, nullptr, nullptr, &err);
+  if (rc < 0) {
+    free(buf);
+    s->fail_grpc++;
+    if (!bad_sig.empty()) return fail(TFSC_E_INVALID, "%s", bad_sig.c_str());
+    return fail(rc, "%s", err.c_str());
+  }
+  *resp = buf;
+  *resp_len = total;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ REST ------
+static const char* state_name(int st) {
+  switch (st) {
+    case TFSC_STATE_START: return "START";
+    case TFSC_STATE_LOADING: return "LOADING";
+    case TFSC_STATE_AVAILABLE: return "AVAILABLE";
+    case TFSC_STATE_UNLOADING: return "UNLOADING";
+    case TFSC_STATE_END: return "END";
+    default: return "UNKNOWN";
+  }
+}
+
+static int http_for(int rc) {
+  switch (rc) {
+    case TFSC_E_INVALID: return 400;
+    case TFSC_E_NOT_FOUND: return 404;
+    case TFSC_E_TIMEOUT: return 504;
+    case TFSC_E_EXHAUSTED: return 507;
+    case TFSC_E_EMPTY_RING: return 503;
+    default: return 500;
+  }
+}
+
+static void set_resp(const std::string& body, void** resp, size_t* resp_len) {
+  char* b = (char*)malloc(body.size() + 1);
+  memcpy(b, body.data(), body.size());
+  b[body.size()] = 0;
+  *resp = b;
+  *resp_len = body.size();
+}
+
+static std::string error_json(const std::string& msg) {
+  std::string s = "{ \"error\": ";
+  json_escape(msg, &s);
+  s += " }";
+  return s;
+}
+
+// flatten a (nested, rectangular) JSON array of numbers
+static bool flatten(const Json& j, size_t depth, std::vector<int64_t>* shape, std::vector<float>* out, std::string* err) {
+  if (j.type == Json::Num) {
+    if (shape->size() > depth) {
+      *err = "ragged tensor";
+      return false;
+    }
+    out->push_back((float)j.num);
+    return true;
+  }
+  if (j.type != Json::Arr) {
+    *err = "tensor values must be numbers or nested arrays of numbers";
+    return false;
+  }
+  if (shape->size() == depth) shape->push_back((int64_t)j.arr.size());
+  else if ((*shape)[depth] != (int64_t)j.arr.size()) {
+    *err = "ragged tensor";
+    return false;
+  }
+  for (auto& e : j.arr)
+    if (!flatten(e, depth + 1, shape, out, err)) return false;
+  return true;
+}
+
+static void write_tensor_json(const float* v, const std::vector<int64_t>& shape, size_t dim, size_t* idx, std::string* s) {
+  if (dim == shape.size()) {
+    json_float(v[(*idx)++], s);
+    return;
+  }
+  *s += "[";
+  for (int64_t i = 0; i < shape[dim]; ++i) {
+    if (i) *s += ", ";
+    write_tensor_json(v, shape, dim + 1, idx, s);
+  }
+  *s += "]";
+}
+
+int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const void* body, size_t body_len,
+                     int* http_status, void** resp, size_t* resp_len) {
+  if (!s || !method || !url || !http_status || !resp || !resp_len) return fail(TFSC_E_INVALID, "rest_handle: bad arguments");
+  s->req_rest++;  // promRequestsTotal{rest}, tfservingproxy.go:96
+  std::string name, version;
+  const std::string u(url);
+  int st = match_rest_url(u, &name, &version);
+  if (st != 200) {  // :99-124
+    s->fail_rest++;
+    *http_status = st;
+    set_resp(rest_error_body(st), resp, resp_len);
+    return 0;
+  }
+  // what follows "/versions/<v>" selects the TF-Serving verb
+  size_t vpos = u.find(version, u.find('/', 11));
+  std::string tail = u.substr(vpos + version.size());
+  size_t qpos = tail.find('?');
+  if (qpos != std::string::npos) tail.resize(qpos);
+  Node* node;
+  ModelId id;
+  int rc = resolve(s, name, version, &node, &id);
+  auto fail_http = [&](int code, const std::string& msg) {
+    s->fail_rest++;
+    *http_status = code;
+    set_resp(error_json(msg), resp, resp_len);
+    return 0;
+  };
+  if (rc < 0) return fail_http(http_for(rc), tfsc_last_error());
+  std::string err;
+  const std::string m(method);
+  if (m == "GET" && (tail.empty() || tail == "/")) {
+    // the request passes through handleModelRequest (fetchModel) before TF-Serving answers
+    rc = node->fetch(id, nullptr, &err);
+    if (rc < 0) return fail_http(http_for(rc), err);
+    int stt = node->status(id);
+    std::string b = "{\n \"model_version_status\": [\n  {\n   \"version\": \"" + std::to_string(id.version) +
+                    "\",\n   \"state\": \"" + state_name(stt) +
+                    "\",\n   \"status\": {\n    \"error_code\": \"OK\",\n    \"error_message\": \"\"\n   }\n  }\n ]\n}\n";
+    *http_status = 200;
+    set_resp(b, resp, resp_len);
+    return 0;
+  }
+  if (m == "POST" && tail == ":predict") {
+    Json req;
+    bool parsed = json_parse(std::string((const char*)body, body_len), &req, &err) && req.type == Json::Obj;
+    const Json* instances = parsed ? req.get("instances") : nullptr;
+    const Json* inputs = parsed ? req.get("inputs") : nullptr;
+    std::vector<int64_t> shape;
+    std::vector<float> flat;
+    std::string input_key;
+    bool ok = parsed && ((instances != nullptr) != (inputs != nullptr));
+    if (parsed && !ok) err = "JSON body must contain exactly one of 'instances' (row format) or 'inputs' (columnar)";
+    if (ok && instances) {
+      const Json* src = instances;
+      Json unwrapped;
+      // row format: a list of instances; an instance may be {"<input>": value}
+      if (instances->type == Json::Arr && !instances->arr.empty() && instances->arr[0].type == Json::Obj) {
+        unwrapped.type = Json::Arr;
+        for (auto& inst : instances->arr) {
+          if (inst.type != Json::Obj || inst.obj.size() != 1) {
+            ok = false;
+            err = "each instance object must name exactly one input";
+            break;
+          }
+          input_key = inst.obj[0].first;
+          unwrapped.arr.push_back(inst.obj[0].second);
+        }
+        src = &unwrapped;
+      }
+      if (ok) ok = flatten(*src, 0, &shape, &flat, &err);
+    } else if (ok) {
+      const Json* src = inputs;
+      if (inputs->type == Json::Obj) {
+        if (inputs->obj.size() != 1) {
+          ok = false;
+          err = "'inputs' object must name exactly one input";
+        } else {
+          input_key = inputs->obj[0].first;
+          src = &inputs->obj[0].second;
+        }
+      }
+      if (ok) ok = flatten(*src, 0, &shape, &flat, &err);
+    }
+    if (!ok || flat.empty()) {
+      std::string e2;
+      rc = node->fetch(id, nullptr, &e2);  // residency is ensured before the body is looked at
+      if (rc < 0) return fail_http(http_for(rc), e2);
+      return fail_http(400, err.empty() ? "empty request" : err);
+    }
+    std::vector<float> y;
+    std::vector<int64_t> oshape;
+    std::string bad_sig;
+    auto alloc = [&](const ModelDesc& d, int64_t rows) -> void* {
+      if (!input_key.empty() && input_key != d.input_name) {
+        bad_sig = "input '" + input_key + "' does not match the model signature (expects '" + d.input_name + "')";
+        return nullptr;
+      }
+      out_shape(d, rows, shape, &oshape);
+      int64_t on = 1;
+      for (auto v : oshape) on *= v;
+      y.resize((size_t)on);
+      return y.data();
+    };
+    rc = node->predict_host(id, flat.data(), (int64_t)flat.size(), alloc, nullptr, nullptr, &err);
+    if (rc < 0) return fail_http(bad_sig.empty() ? http_for(rc) : 400, bad_sig.empty() ? err : bad_sig);
+    // TF-Serving's writer: 4-space indent, arrays on one line, closing bracket on its own line
+    std::string b = std::string("{\n    \"") + (instances ? "predictions" : "outputs") + "\": ";
+    size_t idx = 0;
+    if (oshape.empty()) {
+      json_float(y[0], &b);
+      b += "\n}";
+    } else {
+      std::string t;
+      write_tensor_json(y.data(), oshape, 0, &idx, &t);
+      t.pop_back();  // drop the final ']' and re-emit it TF-Serving style
+      b += t + "\n    ]\n}";
+    }
+    *http_status = 200;
+    set_resp(b, resp, resp_len);
+    return 0;
+  }
+  if (m == "GET" && tail == "/metadata") {
+    ModelDesc d;
+    rc = node->describe(id, &d, nullptr, &err);
+    if (rc < 0) return fail_http(http_for(rc), err);
+    std::string dim = d.tmpl == Template::Affine ? "" : std::to_string(d.in_dim);
+    std::string odim = d.tmpl == Template::Affine ? "" : std::to_string(d.out_dim);
+    auto tensor_info = [](const std::string& key, const std::string& last_dim) {
+      std::string t = "\"" + key + "\": {\"dtype\": \"DT_FLOAT\", \"tensor_shape\": {\"dim\": [{\"size\": \"-1\", \"name\": \"\"}";
+      if (!last_dim.empty()) t += ", {\"size\": \"" + last_dim + "\", \"name\": \"\"}";
+      t += "], \"unknown_rank\": false}, \"name\": \"" + key + ":0\"}";
+      return t;
+    };
+    std::string b = "{\n\"model_spec\": {\"name\": ";
+    json_escape(name, &b);
+    b += ", \"signature_name\": \"\", \"version\": \"" + std::to_string(id.version) + "\"},\n\"metadata\": {\"signature_def\": {\"signature_def\": {\"serving_default\": {\"inputs\": {" +
+         tensor_info(d.input_name, dim) + "}, \"outputs\": {" + tensor_info(d.output_name, odim) +
+         "}, \"method_name\": \"tensorflow/serving/predict\"}}}}\n}\n";
+    *http_status = 200;
+    set_resp(b, resp, resp_len);
+    return 0;
+  }
+  if (m == "POST" && (tail == ":classify" || tail == ":regress")) {
+    rc = node->fetch(id, nullptr, &err);
+    if (rc < 0) return fail_http(http_for(rc), err);
+    return fail_http(400, "Expected classification/regression signature; model " + name + " exports a predict signature only");
+  }
+  return fail_http(400, "Malformed request: " + m + " " + u);
+}
+
+int tfsc_predict_device(tfsc_server* s, int node, const char* model_name, int64_t version, const void* x,
+                        int64_t rows, void* y, void* stream) {
+  Node* n = node_at(s, node);
+  if (!n || !model_name) return TFSC_E_INVALID;
+  std::string err;
+  int rc = n->predict_device({model_name, version}, x, rows, y, (cudaStream_t)stream, &err);
+  if (rc < 0) return fail(rc, "%s", err.c_str());
+  return 0;
+}
+
+int tfsc_node_sync(tfsc_server* s, int node) {
+  Node* n = node_at(s, node);
+  if (!n) return TFSC_E_INVALID;
+  return n->sync();
+}
+
+int tfsc_get_stats(tfsc_server* s, int node, tfsc_stats* out) {
+  if (!s || !out) return fail(TFSC_E_INVALID, "get_stats: bad arguments");
+  memset(out, 0, sizeof *out);
+  if (node >= 0) {
+    Node* n = node_at(s, node);
+    if (!n) return TFSC_E_INVALID;
+    n->stats(out);
+  } else {
+    for (auto& n : s->nodes) n->stats(out);
+  }
+  out->proxy_requests_rest = s->req_rest;
+  out->proxy_requests_grpc = s->req_grpc;
+  out->proxy_failures_rest = s->fail_rest;
+  out->proxy_failures_grpc = s->fail_grpc;
+  out->kernel_launches = kernel_launch_count();
+  return 0;
+}
+
+// ------------------------------------------------------------------ raw kernel entries ------
+static int check_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(TFSC_E_NO_DEVICE, "no CUDA device available: this library has no CPU fallback");
+  }
+  return 0;
+}
+
+int tfsc_k_affine(const float* x, float* y, int64_t n, const float* a, const float* b, void* stream) {
+  if (int rc = check_device()) return rc;
+  cudaError_t e = launch_affine(x, y, n, a, b, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "affine: %s", cudaGetErrorString(e));
+}
+
+int tfsc_k_dense(const float* x, const float* w, const float* b, float* y, int rows, int k, int n, int relu,
+                 float* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_device()) return rc;
+  cudaError_t e = launch_dense(x, w, b, y, rows, k, n, relu != 0, workspace, workspace_bytes, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "dense: %s", cudaGetErrorString(e));
+}
+
+size_t tfsc_k_dense_workspace(int rows, int k, int n) { return dense_workspace_bytes(rows, k, n); }
+
+}  // extern "C"

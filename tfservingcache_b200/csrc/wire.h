@@ -1,0 +1,49 @@
+// Protobuf wire codec for the messages on the Predict path, hand-rolled:
+// zero-copy views into the request bytes (tensor_content / packed float_val point into the
+// caller's buffer) and a response writer that leaves a hole for the executor to fill.
+// Field numbers: proto/tensorflow/serving/predict.pb.go:30-43,98-100; model.pb.go:27-91;
+// proto/tensorflow/core/framework/tensor.pb.go:25-68; tensor_shape.pb.go:38-96.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace tfsc {
+
+struct TensorView {
+  std::string name;
+  int dtype = 0;
+  std::vector<int64_t> shape;
+  const uint8_t* content = nullptr;  // tensor_content (field 4)
+  size_t content_len = 0;
+  const uint8_t* packed_f32 = nullptr;  // packed float_val (field 5, wire type 2)
+  size_t packed_f32_len = 0;
+  std::vector<float> loose_f32;  // unpacked float_val entries / double_val / int_val converted
+  int64_t num_elements() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+struct PredictRequestView {
+  std::string model_name, signature_name;
+  bool has_version = false;
+  int64_t version = 0;
+  std::vector<TensorView> inputs;
+  std::vector<std::string> output_filter;
+};
+
+bool decode_predict_request(const void* data, size_t len, PredictRequestView* out, std::string* err);
+// fp32 elements of a DT_FLOAT tensor; `scratch` is used when the data is not contiguous in the
+// request (unpacked float_val, scalar broadcast).
+bool tensor_f32(const TensorView& t, const float** data, int64_t* n, std::vector<float>* scratch, std::string* err);
+
+// Serialized PredictResponse{outputs{name: TensorProto{DT_FLOAT, shape, float_val}}, model_spec}
+// split around the float payload: prefix | n_floats*4 payload bytes | suffix.
+void predict_response_frame(const std::string& model_name, int64_t version, const std::string& signature_name,
+                            const std::string& output_name, const std::vector<int64_t>& shape, std::string* prefix,
+                            std::string* suffix);
+
+}  // namespace tfsc
