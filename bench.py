@@ -1,0 +1,458 @@
+#!/usr/bin/env python
+"""bench.py -- predict QPS of the route -> ensure-resident -> predict hot path on a Zipf
+multi-model mix (BASELINE.json metric), one process per GPU.
+
+Workload (config.workload): the per-GPU shard of BASELINE.json configs[2] -- the configuration the
+north_star target is quoted on: N GPUs serve 125*N per-tenant 3-layer MLPs (9216^4 fp32,
+1 019 326 464 B each), Zipf(alpha=1.0) request stream, ring replicas = min(2, N).  Per-GPU work is
+fixed as N grows (weak scaling); at N=8 it is exactly configs[2] (1000 models, replicas 2).
+
+A "step" is one batcher tick: `--tick` (default 1024) requests per GPU drawn from the seeded Zipf
+trace, routed with the consistent-hash ring, grouped per resident model and executed.
+  value  : whole-job req/s with the step's inputs already resident in HBM (device pointers through
+           tfsc_predict_device), timed with CUDA events on the launching stream.
+  e2e    : the same ticks through the public C ABI call tfsc_predict() with HOST buffers from
+           `--clients` closed-loop client threads (H2D of inputs + D2H of results inside the timed
+           region), plus p50/p99 latency.
+  --impl reference : the reference's CPU path restated (ring -> LRU/top-N residency -> per-request,
+           unbatched fp32 forward on all host cores with torch-CPU), on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIMS = [9216, 9216, 9216, 9216]
+MODEL_BYTES = 1019326464
+MODELS_PER_GPU = 125
+IN_DIM, OUT_DIM = DIMS[0], DIMS[-1]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tick", type=int, default=1024, help="requests per GPU per step")
+    ap.add_argument("--clients", type=int, default=1024, help="closed-loop client threads per GPU (e2e)")
+    ap.add_argument("--models-per-gpu", type=int, default=MODELS_PER_GPU)
+    ap.add_argument("--arena-gib", type=float, default=160.0)
+    ap.add_argument("--host-gib", type=float, default=0.0, help="pinned host tier per GPU (0 = auto)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    ap.add_argument("--cpu-sample", type=int, default=48, help="requests in the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dims", type=int, nargs="*", default=None, help="override model dims (debug only)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------- workload ------
+def splitmix(i: np.ndarray) -> np.ndarray:
+    z = (i.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15))
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42):
+    """Global request stream + ring routing, identical on every rank (no communication)."""
+    import tfservingcache_b200 as t
+    from oracle.zipf import zipf_trace  # trace generator only (test/bench infrastructure)
+    n_models = models_per_gpu * n_gpus
+    replicas = min(2, n_gpus)
+    members = [f"gpu{i}:0:0" for i in range(n_gpus)]
+    cluster = t.ClusterConnection(replicas)
+    cluster.update([t.ServingService.from_string(m) for m in members])
+    owners = np.empty((n_models, replicas), dtype=np.int32)
+    for j in range(n_models):
+        nodes = cluster.find_node_for_key(t.model_key(f"m{j}", "1"))  # nodeForKey, taskhandler.go:84-92
+        owners[j] = [int(s.host[3:]) for s in nodes]
+    total = tick * n_gpus * n_steps
+    trace = zipf_trace(n_models, total, 1.0, seed)
+    # "Pick random node" (taskhandler.go:91) with a counter-based RNG so all ranks agree
+    pick = (splitmix(np.arange(total)) % np.uint64(replicas)).astype(np.int64)
+    dest = owners[trace, pick]
+    return dict(n_models=n_models, replicas=replicas, members=members, trace=trace, dest=dest, owners=owners)
+
+
+def step_groups(wl, rank, step, tick_global):
+    """Requests of `step` owned by `rank`, grouped per model: [(model, count)] in first-arrival order."""
+    lo, hi = step * tick_global, (step + 1) * tick_global
+    mine = wl["trace"][lo:hi][wl["dest"][lo:hi] == rank]
+    order, counts = [], {}
+    for m in mine.tolist():
+        if m not in counts:
+            order.append(m)
+            counts[m] = 0
+        counts[m] += 1
+    return mine, [(m, counts[m]) for m in order]
+
+
+def algorithmic_bytes(groups, dims):
+    """per launch of one dense layer = W + bias + rows*(in+out)*4; rows > 8 are run as
+    ceil(rows/8) passes, each streaming W once."""
+    total, launches = 0, 0
+    for _m, rows in groups:
+        r = rows
+        while r > 0:
+            rr = min(8, r)
+            for l in range(len(dims) - 1):
+                total += dims[l] * dims[l + 1] * 4 + dims[l + 1] * 4 + rr * (dims[l] + dims[l + 1]) * 4
+                launches += 1
+            r -= rr
+    return total, launches
+
+
+# ---------------------------------------------------------------------------------- clocks ------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- b200 impl ------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import tfservingcache_b200 as t
+    from tfservingcache_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    assert torch.cuda.is_available(), "bench.py needs a B200; the library has no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dims = args.dims or DIMS
+    in_dim, out_dim = dims[0], dims[-1]
+    model_bytes = sum(dims[i] * dims[i + 1] * 4 + dims[i + 1] * 4 for i in range(len(dims) - 1))
+    W, K = args.warmup, args.steps
+    e2e_steps = args.e2e_steps or K
+    n_steps_total = W + K + W + e2e_steps
+    wl = build_workload(world, args.models_per_gpu, args.tick, n_steps_total)
+    tick_global = args.tick * world
+
+    free_b, _tot = torch.cuda.mem_get_info()
+    arena = min(int(args.arena_gib * 2**30), int(free_b * 0.9))
+    my_models = sorted({int(m) for m in np.unique(wl["trace"][wl["dest"] == rank])})
+    host_gib = args.host_gib
+    if host_gib <= 0:
+        avail_kb = 0
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                avail_kb = int(line.split()[1])
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        host_gib = min(len(my_models) * model_bytes / 2**30 * 1.02 + 1, avail_kb / 2**20 * 0.7 / max(local_world, 1))
+    cfg = {"modelProvider.type": "synthetic", "modelProvider.synthetic.dims": dims,
+           "modelProvider.synthetic.count": wl["n_models"], "modelProvider.synthetic.namePrefix": "m",
+           "modelProvider.synthetic.threads": max(4, min(32, (os.cpu_count() or 8) // max(world, 1))),
+           "gpu.devices": [local], "gpu.arenaBytes": arena, "gpu.maxBatch": 8, "gpu.maxRequestRows": 4096,
+           "gpu.stagingSlots": 4, "modelCache.size": int(host_gib * 2**30), "serving.maxConcurrentModels": 1 << 20,
+           "proxy.replicasPerModel": wl["replicas"], "gpu.members": wl["members"], "gpu.localMembers": [wl["members"][rank]],
+           "proxy.seed": 1}
+    srv = t.Server(cfg)
+
+    # page every model this rank owns into HBM once (cold loads are not part of the steady-state metric;
+    # with replicas=2 the owned set can exceed the arena and LRU paging continues inside the timed steps)
+    t_load = time.time()
+    for m in my_models:
+        srv.ensure(0, f"m{m}", 1)
+    load_s = time.time() - t_load
+
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    max_rows = args.tick * 4
+    x_dev = torch.randn(max_rows, in_dim, device="cuda", dtype=torch.float32)
+    y_dev = torch.empty(max_rows, out_dim, device="cuda", dtype=torch.float32)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def device_step(step):
+        _mine, groups = step_groups(wl, rank, step, tick_global)
+        off = 0
+        for m, rows in groups:
+            rc = srv.ensure(0, f"m{m}", 1)  # route -> ensure-resident (hit unless the LRU paged it out)
+            srv.predict_device(0, f"m{m}", 1, x_dev.data_ptr() + off * in_dim * 4, rows, y_dev.data_ptr() + off * out_dim * 4, sptr)
+            off += rows
+        return groups
+
+    # ---- value: inputs resident in HBM ----------------------------------------------------------
+    for s in range(W):
+        device_step(s)
+    barrier()
+    flush.fill_(1)  # inputs (>= 1 GB of weights per launch) already exceed L2; flush once anyway
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.lib.tfsc_kernel_launches()
+    st0 = srv.stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    alg_bytes, n_req, n_dense = 0, 0, 0
+    for s in range(W, W + K):
+        groups = device_step(s)
+        b, l = algorithmic_bytes(groups, dims)
+        alg_bytes += b
+        n_dense += l
+        n_req += sum(r for _m, r in groups)
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = _lib.lib.tfsc_kernel_launches() - launches0
+    st1 = srv.stats()
+
+    # ---- e2e: host buffers through tfsc_predict (C ABI), closed-loop clients ----------------------
+    lg = C.CDLL(os.path.join(ROOT, "tools", "libtfsc_loadgen.so"))
+    lg.tfsc_loadgen_run.restype = C.c_int64
+    names = b"".join(f"m{j}".encode().ljust(16, b"\0") for j in range(wl["n_models"]))
+    n_inputs = 256
+    inputs_h = torch.randn(n_inputs, in_dim).pin_memory()
+    outputs_h = torch.empty(args.clients, out_dim).pin_memory()
+    predict_ptr = C.cast(_lib.lib.tfsc_predict, C.c_void_p)
+
+    def e2e_run(step_lo, step_hi, want_lat):
+        req = np.concatenate([step_groups(wl, rank, s, tick_global)[0] for s in range(step_lo, step_hi)]).astype(np.int32)
+        lat = np.zeros(len(req), np.float32)
+        el = C.c_double()
+        failed = lg.tfsc_loadgen_run(predict_ptr, C.c_void_p(srv._h), names, 16, b"1", req.ctypes.data_as(C.c_void_p),
+                                     C.c_int64(len(req)), C.c_void_p(inputs_h.data_ptr()), C.c_int64(n_inputs), in_dim,
+                                     C.c_void_p(outputs_h.data_ptr()), out_dim, args.clients,
+                                     lat.ctypes.data_as(C.c_void_p) if want_lat else None, C.byref(el))
+        return len(req), failed, el.value, lat
+
+    e0 = W + K
+    e2e_run(e0, e0 + W, False)
+    barrier()
+    ste0 = srv.stats()
+    n_e2e, failed, el_s, lat = e2e_run(e0 + W, e0 + W + e2e_steps, True)
+    torch.cuda.synchronize()
+    ste1 = srv.stats()
+    if world > 1:
+        tt = torch.tensor([elapsed_ms, el_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms, el_s = float(tt[0]), float(tt[1])
+        cc = torch.tensor([n_req, n_e2e, launches, alg_bytes, failed, n_dense], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        n_req_all, n_e2e_all, launches_all, failed_all = int(cc[0]), int(cc[1]), int(cc[2]), int(cc[4])
+    else:
+        n_req_all, n_e2e_all, launches_all, failed_all = n_req, n_e2e, launches, failed
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+    achieved = alg_bytes / (elapsed_ms * 1e-3) / 1e9  # this rank's dense launches are the whole timed region
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dense_stream_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_reference(args.cpu_sample, dims, warm=4)
+
+    if rank == 0:
+        value = n_req_all / (elapsed_ms * 1e-3)
+        e2e_val = n_e2e_all / el_s
+        line = {
+            "metric": "predict_qps", "value": round(value, 1), "unit": "req/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(elapsed_ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[2] per-GPU shard: {args.models_per_gpu} per-tenant 3-layer MLP "
+                                   f"({'x'.join(map(str, dims))} fp32, {model_bytes} B) per GPU, Zipf alpha=1.0, ring replicas={wl['replicas']}; "
+                                   f"at 8 GPUs = configs[2] (1000 models)",
+                       "models_total": wl["n_models"], "tick_requests_per_gpu": args.tick, "max_rows_per_pass": 8,
+                       "l2": "inputs larger than L2 (>=1 GB of weights streamed per model pass); L2 flushed before timing",
+                       "arena_gib": round(arena / 2**30, 1), "host_tier_gib": round(host_gib, 1), "cold_load_s": round(load_s, 1)},
+            "e2e": {"value": round(e2e_val, 1), "unit": "req/s",
+                    "h2d_bytes_per_step": int((ste1["h2d_input_bytes"] - ste0["h2d_input_bytes"] + ste1["h2d_weight_bytes"] - ste0["h2d_weight_bytes"]) / e2e_steps),
+                    "d2h_bytes_per_step": int((ste1["d2h_output_bytes"] - ste0["d2h_output_bytes"]) / e2e_steps),
+                    "clients_per_gpu": args.clients, "steps": e2e_steps, "failed": failed_all,
+                    "p50_ms": round(float(np.percentile(lat, 50)) / 1e3, 3), "p99_ms": round(float(np.percentile(lat, 99)) / 1e3, 3),
+                    "mean_batch_rows": round((ste1["batched_rows"] - ste0["batched_rows"]) / max(1, ste1["batches"] - ste0["batches"]), 2)},
+            "hbm_cache_hit_pct": round(100.0 * (st1["cache_hits_total"] - st0["cache_hits_total"]) / max(1, st1["cache_total"] - st0["cache_total"]), 2),
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": traffic, "kernel": "dense_stream_kernel<R> (fused xW+b+ReLU, split-K)", "peak_source": peak_src,
+                         "launches_timed": n_dense, "avg_launch_us": round(elapsed_ms * 1e3 / max(1, n_dense), 2)},
+        }
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    srv.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------- reference arm ------
+def cpu_reference(n_sample, dims, warm=4, steps=None):
+    """The reference's path restated on the host CPU (oracle): ring lookup -> LRU + top-N residency
+    (hit path) -> ONE unbatched fp32 forward per request (the reference never batches) with
+    torch-CPU on all host cores -- the stand-in for CPU TF-Serving (absent from the box)."""
+    import torch
+
+    from oracle import cachemanager as ocm
+    from oracle import models as omodels
+    from oracle import ring as oring
+    from oracle.lrucache import Model, ModelIdentifier
+    from oracle.zipf import zipf_trace
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    liborc = C.CDLL(os.path.join(ROOT, "oracle", "liboracle_ref.so"))
+    n_models = MODELS_PER_GPU
+    trace = zipf_trace(n_models, 4096, 1.0, 42)
+    # bounded sample: the requests that touch the 12 most popular models of the trace
+    top = [int(m) for m in np.argsort(-np.bincount(trace, minlength=n_models))[:12]]
+    sample = [int(m) for m in trace if int(m) in top][: n_sample + warm]
+    man = omodels.mlp_manifest(dims)
+
+    def synth(j):
+        blob = np.empty(man["weights_bytes"] // 4, np.float32)
+
+        def fill(tid, off, n, scale):
+            per = (n + 15) // 16
+            ths = []
+            for c in range(16):
+                lo, hi = c * per, min(n, (c + 1) * per)
+                if lo < hi:
+                    th = threading.Thread(target=liborc.oracle_synth_fill, args=(
+                        C.c_void_p(blob.ctypes.data + (off + lo) * 4), C.c_uint32(1000 + j), C.c_uint32(tid), C.c_uint64(lo),
+                        C.c_uint64(hi - lo), C.c_float(scale)))
+                    th.start()
+                    ths.append(th)
+            [th.join() for th in ths]
+        layers = []
+        for l, L in enumerate(man["layers"]):
+            fill(2 * l, L["w_offset"] // 4, L["in"] * L["out"], omodels.weight_scale(L["in"]))
+            fill(2 * l + 1, L["b_offset"] // 4, L["out"], omodels.BIAS_SCALE)
+            w = torch.from_numpy(blob[L["w_offset"] // 4: L["w_offset"] // 4 + L["in"] * L["out"]].reshape(L["in"], L["out"]))
+            b = torch.from_numpy(blob[L["b_offset"] // 4: L["b_offset"] // 4 + L["out"]])
+            layers.append((w, b, L["activation"] == "relu"))
+        return blob, layers
+
+    weights = {j: synth(j) for j in top}
+
+    class Prov:
+        def model_size(self, name, ver):
+            return man["weights_bytes"]
+
+        def load_model(self, name, ver):
+            return Model(ModelIdentifier(name, ver), f"{name}/{ver}", man["weights_bytes"])
+
+    cluster = oring.ClusterConnection(1)
+    cluster.update([oring.ServingService("gpu0", 0, 0)])
+    cm = ocm.CacheManager(Prov(), 1 << 50, 1 << 20)
+    x = torch.randn(1, dims[0])
+
+    def one(j):
+        oring.node_for_key(cluster, f"m{j}", "1", lambda n: 0)
+        cm.handle_model_request(f"m{j}", "1")
+        h = x
+        with torch.no_grad():
+            for w, b, relu in weights[j][1]:
+                h = torch.addmm(b, h, w)
+                if relu:
+                    h = torch.relu_(h)
+        return h
+
+    for j in sample[:warm]:
+        one(j)
+    t0 = time.perf_counter()
+    for j in sample[warm:]:
+        one(j)
+    dt = time.perf_counter() - t0
+    n = len(sample) - warm
+    return {"value": round(n / dt, 2), "unit": "req/s", "cores": cores, "kind": "port",
+            "sample": f"{n} unbatched requests (1 row each) of the Zipf trace restricted to its 12 most popular of {n_models} "
+                      f"models, all cached+resident (hit path), torch-CPU fp32 addmm, {cores} threads; restated reference path "
+                      f"(ring -> LRU -> forward), TF-Serving itself is not available",
+            "seconds": round(dt, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dims = args.dims or DIMS
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # each "step" is a bounded sample of the workload; K steps + W warm-up end within minutes
+    per_step = max(4, args.cpu_sample // 4)
+    base = cpu_reference(per_step * args.steps, dims, warm=max(1, per_step * args.warmup // 4))
+    model_bytes = sum(dims[i] * dims[i + 1] * 4 + dims[i + 1] * 4 for i in range(len(dims) - 1))
+    line = {"impl": "reference", "metric": "predict_qps", "value": base["value"], "unit": "req/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * base["seconds"] / args.steps, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[2] per-GPU shard: {MODELS_PER_GPU} per-tenant 3-layer MLP "
+                                   f"({'x'.join(map(str, dims))} fp32, {model_bytes} B) per GPU, Zipf alpha=1.0; CPU reference path, "
+                                   f"bounded sample of {per_step} requests per step"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "req/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
