@@ -15,7 +15,7 @@ trace, routed with the consistent-hash ring, grouped per resident model and exec
            `--clients` closed-loop client threads (H2D of inputs + D2H of results inside the timed
            region), plus p50/p99 latency.
   --impl reference : the reference's CPU path restated (ring -> LRU/top-N residency -> per-request,
-           unbatched fp32 forward on all host cores with torch-CPU), on a bounded sample.
+           unbatched fp32 forward on all host cores, oracle C), on a bounded sample.
 """
 from __future__ import annotations
 
@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
     ap.add_argument("--cpu-sample", type=int, default=48, help="requests in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident part alone")
     ap.add_argument("--dims", type=int, nargs="*", default=None, help="override model dims (debug only)")
     return ap.parse_args()
 
@@ -276,10 +277,14 @@ def run_b200(args):
         return len(req), failed, el.value, lat
 
     e0 = W + K
-    e2e_run(e0, e0 + W, False)
+    if not args.skip_e2e:
+        e2e_run(e0, e0 + W, False)
     barrier()
     ste0 = srv.stats()
-    n_e2e, failed, el_s, lat = e2e_run(e0 + W, e0 + W + e2e_steps, True)
+    if args.skip_e2e:
+        n_e2e, failed, el_s, lat = 0, 0, 1.0, np.zeros(1, np.float32)
+    else:
+        n_e2e, failed, el_s, lat = e2e_run(e0 + W, e0 + W + e2e_steps, True)
     torch.cuda.synchronize()
     ste1 = srv.stats()
     if world > 1:
@@ -345,18 +350,15 @@ def run_b200(args):
 # ---------------------------------------------------------------------------- reference arm ------
 def cpu_reference(n_sample, dims, warm=4, steps=None):
     """The reference's path restated on the host CPU (oracle): ring lookup -> LRU + top-N residency
-    (hit path) -> ONE unbatched fp32 forward per request (the reference never batches) with
-    torch-CPU on all host cores -- the stand-in for CPU TF-Serving (absent from the box)."""
-    import torch
-
+    (hit path) -> ONE unbatched fp32 forward per request (the reference never batches) with the
+    oracle's multi-threaded C GEMV on all host cores -- the stand-in for CPU TF-Serving (absent)."""
     from oracle import cachemanager as ocm
     from oracle import models as omodels
     from oracle import ring as oring
     from oracle.lrucache import Model, ModelIdentifier
     from oracle.zipf import zipf_trace
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = min(os.cpu_count() or 1, 256)
     liborc = C.CDLL(os.path.join(ROOT, "oracle", "liboracle_ref.so"))
     n_models = MODELS_PER_GPU
     trace = zipf_trace(n_models, 4096, 1.0, 42)
@@ -365,13 +367,21 @@ def cpu_reference(n_sample, dims, warm=4, steps=None):
     sample = [int(m) for m in trace if int(m) in top][: n_sample + warm]
     man = omodels.mlp_manifest(dims)
 
+    I4 = C.c_int64 * len(dims)
+    I3 = C.c_int64 * (len(dims) - 1)
+    c_dims = I4(*dims)
+    c_woff = I3(*[L["w_offset"] for L in man["layers"]])
+    c_boff = I3(*[L["b_offset"] for L in man["layers"]])
+    c_relu = (C.c_int * (len(dims) - 1))(*[1 if L["activation"] == "relu" else 0 for L in man["layers"]])
+    liborc.oracle_mlp_forward_mt.restype = C.c_int
+
     def synth(j):
         blob = np.empty(man["weights_bytes"] // 4, np.float32)
 
         def fill(tid, off, n, scale):
-            per = (n + 15) // 16
+            per = (n + 31) // 32
             ths = []
-            for c in range(16):
+            for c in range(32):
                 lo, hi = c * per, min(n, (c + 1) * per)
                 if lo < hi:
                     th = threading.Thread(target=liborc.oracle_synth_fill, args=(
@@ -380,14 +390,10 @@ def cpu_reference(n_sample, dims, warm=4, steps=None):
                     th.start()
                     ths.append(th)
             [th.join() for th in ths]
-        layers = []
         for l, L in enumerate(man["layers"]):
             fill(2 * l, L["w_offset"] // 4, L["in"] * L["out"], omodels.weight_scale(L["in"]))
             fill(2 * l + 1, L["b_offset"] // 4, L["out"], omodels.BIAS_SCALE)
-            w = torch.from_numpy(blob[L["w_offset"] // 4: L["w_offset"] // 4 + L["in"] * L["out"]].reshape(L["in"], L["out"]))
-            b = torch.from_numpy(blob[L["b_offset"] // 4: L["b_offset"] // 4 + L["out"]])
-            layers.append((w, b, L["activation"] == "relu"))
-        return blob, layers
+        return blob
 
     weights = {j: synth(j) for j in top}
 
@@ -401,18 +407,16 @@ def cpu_reference(n_sample, dims, warm=4, steps=None):
     cluster = oring.ClusterConnection(1)
     cluster.update([oring.ServingService("gpu0", 0, 0)])
     cm = ocm.CacheManager(Prov(), 1 << 50, 1 << 20)
-    x = torch.randn(1, dims[0])
+    x = np.random.default_rng(0).standard_normal((1, dims[0])).astype(np.float32)
+    y = np.empty((1, dims[-1]), np.float32)
 
     def one(j):
-        oring.node_for_key(cluster, f"m{j}", "1", lambda n: 0)
-        cm.handle_model_request(f"m{j}", "1")
-        h = x
-        with torch.no_grad():
-            for w, b, relu in weights[j][1]:
-                h = torch.addmm(b, h, w)
-                if relu:
-                    h = torch.relu_(h)
-        return h
+        oring.node_for_key(cluster, f"m{j}", "1", lambda n: 0)   # taskhandler.go:84-92
+        cm.handle_model_request(f"m{j}", "1")                    # cachemanager.go:294-309 (hit path)
+        rc = liborc.oracle_mlp_forward_mt(C.c_void_p(weights[j].ctypes.data), len(dims) - 1, c_dims, c_woff, c_boff, c_relu,
+                                          C.c_void_p(x.ctypes.data), C.c_int64(1), C.c_void_p(y.ctypes.data), cores)
+        assert rc == 0
+        return y
 
     for j in sample[:warm]:
         one(j)
@@ -423,8 +427,8 @@ def cpu_reference(n_sample, dims, warm=4, steps=None):
     n = len(sample) - warm
     return {"value": round(n / dt, 2), "unit": "req/s", "cores": cores, "kind": "port",
             "sample": f"{n} unbatched requests (1 row each) of the Zipf trace restricted to its 12 most popular of {n_models} "
-                      f"models, all cached+resident (hit path), torch-CPU fp32 addmm, {cores} threads; restated reference path "
-                      f"(ring -> LRU -> forward), TF-Serving itself is not available",
+                      f"models, all cached+resident (hit path), oracle C fp32 split-K GEMV (AVX2) on {cores} threads; restated reference "
+                      f"path (ring -> LRU -> forward), TF-Serving itself is not available",
             "seconds": round(dt, 2)}
 
 

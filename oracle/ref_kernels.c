@@ -83,3 +83,91 @@ int oracle_mlp_forward(const float* blob, int n_layers, const int64_t* dims, con
     free(cur); free(nxt); free(acc);
     return 0;
 }
+
+/* Multi-threaded forward for the CPU baseline (bench.py cpu_baseline / --impl reference): the
+ * arithmetic TF-Serving's intra-op thread pool would do for a batch-1 request, written the way a
+ * bandwidth-bound GEMV wants it on a many-core host: K is split across threads (each streams a
+ * contiguous block of W rows), private fp32 accumulators, then a reduction. Persistent pthread
+ * pool (no OpenMP runtime in this image's gcc). */
+#include <pthread.h>
+
+typedef struct {
+    const float* W; const float* bias; const float* cur; float* nxt; float* part;
+    int64_t K, N, B; int relu; int T;
+} mt_job;
+
+static struct {
+    int T; int started; int quit;
+    pthread_t* th; pthread_barrier_t go, mid, done; mt_job job;
+} g_pool;
+
+static void mt_phase1(const mt_job* j, int t) {
+    const int64_t k0 = j->K * t / j->T, k1 = j->K * (t + 1) / j->T;
+    float* acc = j->part + (size_t)t * j->B * j->N;
+    for (int64_t i = 0; i < j->B * j->N; ++i) acc[i] = 0.f;
+    for (int64_t k = k0; k < k1; ++k) {
+        const float* wr = j->W + k * j->N;
+        for (int64_t r = 0; r < j->B; ++r) {
+            const float xv = j->cur[r * j->K + k];
+            float* a = acc + r * j->N;
+            for (int64_t n = 0; n < j->N; ++n) a[n] += xv * wr[n];
+        }
+    }
+}
+static void mt_phase2(const mt_job* j, int t) {
+    const int64_t tot = j->B * j->N, i0 = tot * t / j->T, i1 = tot * (t + 1) / j->T;
+    for (int64_t i = i0; i < i1; ++i) {
+        float s = 0.f;
+        for (int tt = 0; tt < j->T; ++tt) s += j->part[(size_t)tt * tot + i];
+        s += j->bias[i % j->N];
+        j->nxt[i] = (j->relu && s < 0.f) ? 0.f : s;
+    }
+}
+static void* mt_worker(void* arg) {
+    const int t = (int)(intptr_t)arg;
+    for (;;) {
+        pthread_barrier_wait(&g_pool.go);
+        if (g_pool.quit) return 0;
+        mt_phase1(&g_pool.job, t);
+        pthread_barrier_wait(&g_pool.mid);
+        mt_phase2(&g_pool.job, t);
+        pthread_barrier_wait(&g_pool.done);
+    }
+}
+static int mt_start(int T) {
+    if (g_pool.started && g_pool.T == T) return 0;
+    if (g_pool.started) return -2;  /* one pool size per process */
+    g_pool.T = T;
+    g_pool.th = (pthread_t*)malloc(sizeof(pthread_t) * T);
+    pthread_barrier_init(&g_pool.go, 0, T); pthread_barrier_init(&g_pool.mid, 0, T); pthread_barrier_init(&g_pool.done, 0, T);
+    for (int t = 1; t < T; ++t) pthread_create(&g_pool.th[t], 0, mt_worker, (void*)(intptr_t)t);
+    g_pool.started = 1;
+    return 0;
+}
+
+int oracle_mlp_forward_mt(const float* blob, int n_layers, const int64_t* dims, const int64_t* w_off,
+                          const int64_t* b_off, const int* relu, const float* x, int64_t B, float* y, int nthreads) {
+    int64_t maxd = 0;
+    for (int l = 0; l <= n_layers; ++l) if (dims[l] > maxd) maxd = dims[l];
+    if (nthreads < 1) nthreads = 1;
+    if (mt_start(nthreads)) return -2;
+    float* cur = (float*)malloc(sizeof(float) * B * maxd);
+    float* nxt = (float*)malloc(sizeof(float) * B * maxd);
+    float* part = (float*)malloc(sizeof(float) * (size_t)nthreads * B * maxd);
+    if (!cur || !nxt || !part) return -1;
+    memcpy(cur, x, sizeof(float) * B * dims[0]);
+    for (int l = 0; l < n_layers; ++l) {
+        mt_job* j = &g_pool.job;
+        j->W = blob + w_off[l] / 4; j->bias = blob + b_off[l] / 4; j->cur = cur; j->nxt = nxt; j->part = part;
+        j->K = dims[l]; j->N = dims[l + 1]; j->B = B; j->relu = relu[l]; j->T = nthreads;
+        pthread_barrier_wait(&g_pool.go);   /* thread 0 = the caller */
+        mt_phase1(j, 0);
+        pthread_barrier_wait(&g_pool.mid);
+        mt_phase2(j, 0);
+        pthread_barrier_wait(&g_pool.done);
+        float* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    memcpy(y, cur, sizeof(float) * B * dims[n_layers]);
+    free(cur); free(nxt); free(part);
+    return 0;
+}

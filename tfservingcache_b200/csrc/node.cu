@@ -28,6 +28,8 @@ bool Node::init(std::string* err) {
   DeviceGuard g(cfg_.device);
   CU_OK(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking), err, false);
   CU_OK(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking), err, false);
+  CU_OK(cudaStreamCreateWithFlags(&in_, cudaStreamNonBlocking), err, false);
+  CU_OK(cudaStreamCreateWithFlags(&out_, cudaStreamNonBlocking), err, false);
   size_t bytes = (size_t)cfg_.arena_bytes;
   if (bytes == 0) {
     size_t fr = 0, tot = 0;
@@ -37,7 +39,11 @@ bool Node::init(std::string* err) {
   CU_OK(cudaMalloc(&slab_, bytes), err, false);
   arena_.init(bytes, 1024);
   slots_.resize(cfg_.slots > 0 ? cfg_.slots : 1);
-  for (auto& s : slots_) CU_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), err, false);
+  for (auto& s : slots_) {
+    CU_OK(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming), err, false);
+    CU_OK(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming), err, false);
+    CU_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), err, false);
+  }
   batcher_ = std::thread([this] { batcher_loop(); });
   completer_ = std::thread([this] { completer_loop(); });
   return true;
@@ -63,6 +69,8 @@ Node::~Node() {
     if (s.act1) cudaFree(s.act1);
     if (s.ws) cudaFree(s.ws);
     if (s.done) cudaEventDestroy(s.done);
+    if (s.in_done) cudaEventDestroy(s.in_done);
+    if (s.k_done) cudaEventDestroy(s.k_done);
   }
   for (auto& kv : stream_scratch_) cudaFree(kv.second.base);
   for (auto& r : retire_) cudaEventDestroy(r.ev);
@@ -76,6 +84,8 @@ Node::~Node() {
   if (slab_) cudaFree(slab_);
   if (compute_) cudaStreamDestroy(compute_);
   if (copy_) cudaStreamDestroy(copy_);
+  if (in_) cudaStreamDestroy(in_);
+  if (out_) cudaStreamDestroy(out_);
 }
 
 cudaEvent_t Node::get_event() {
@@ -546,8 +556,9 @@ int Node::predict_host(const ModelId& id, const void* x, int64_t n_elems, const 
   req.rows = rows;
   {
     std::lock_guard<std::mutex> lk(q_mu_);
+    req.seq = ++seq_;
     auto& q = pending_[req.dm.get()];
-    if (q.empty()) order_.push_back(req.dm.get());
+    if (q.empty()) order_.insert({req.seq, req.dm.get()});
     q.push_back(&req);
   }
   q_cv_.notify_all();
@@ -568,8 +579,10 @@ void Node::batcher_loop() {
       if (stop_) break;
       continue;
     }
-    DeviceModel* m = order_.front();
-    order_.pop_front();
+    // oldest-request-first: requests are served in arrival order, and every request of the same
+    // model that is already queued rides along (up to gpu.maxBatch rows) in the same pass over W
+    DeviceModel* m = order_.begin()->second;
+    order_.erase(order_.begin());
     auto& q = pending_[m];
     std::vector<PredictRequest*> batch;
     int64_t rows = 0;
@@ -581,7 +594,7 @@ void Node::batcher_loop() {
       q.pop_front();
       if (rows >= cfg_.max_batch) break;
     }
-    if (!q.empty()) order_.push_back(m);  // round-robin fairness between models
+    if (!q.empty()) order_.insert({q.front()->seq, m});
     else pending_.erase(m);
     Slot* s = nullptr;
     slot_cv_.wait(lk, [&] {
@@ -616,13 +629,19 @@ void Node::batcher_loop() {
         memcpy(s->h_in + off, r->x, (size_t)r->rows * rin);
         off += (size_t)r->rows * rin;
       }
-      e = cudaMemcpyAsync(s->d_in, s->h_in, off, cudaMemcpyHostToDevice, compute_);
+      // three streams: inputs H2D | kernels | results D2H, chained by events, so the copies of
+      // neighbouring batches overlap the weight-streaming kernels instead of serialising with them
+      e = cudaMemcpyAsync(s->d_in, s->h_in, off, cudaMemcpyHostToDevice, in_);
       h2d_inputs_ += (int64_t)off;
+      if (e == cudaSuccess) e = cudaEventRecord(s->in_done, in_);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(compute_, s->in_done, 0);
       if (e == cudaSuccess && !dm->ready_seen) e = cudaStreamWaitEvent(compute_, dm->ready, 0);
       if (e == cudaSuccess) e = run_model(*dm, s->d_in, rows, s->d_out, s->act0, s->act1, s->ws, s->ws_cap, compute_);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_out, s->d_out, (size_t)rows * rout, cudaMemcpyDeviceToHost, compute_);
+      if (e == cudaSuccess) e = cudaEventRecord(s->k_done, compute_);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(out_, s->k_done, 0);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_out, s->d_out, (size_t)rows * rout, cudaMemcpyDeviceToHost, out_);
       d2h_outputs_ += (int64_t)rows * (int64_t)rout;
-      if (e == cudaSuccess) e = cudaEventRecord(s->done, compute_);
+      if (e == cudaSuccess) e = cudaEventRecord(s->done, out_);
     }
     batches_++;
     batched_rows_ += rows;

@@ -14,6 +14,7 @@
 #include <deque>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -53,6 +54,7 @@ struct PredictRequest {  // one caller blocked in tfsc_predict
   const void* x = nullptr;
   void* y = nullptr;
   int64_t rows = 0;
+  uint64_t seq = 0;  // global arrival order (the batcher serves oldest-request-first)
   int rc = 1;  // 1 = pending
   std::string err;
   std::mutex mu;
@@ -92,7 +94,7 @@ class Node {
     char *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *act0 = nullptr, *act1 = nullptr;
     void* ws = nullptr;
     size_t io_cap = 0, act_cap = 0, ws_cap = 0;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t in_done = nullptr, k_done = nullptr, done = nullptr;
     std::vector<PredictRequest*> reqs;
     std::shared_ptr<DeviceModel> dm;
     bool busy = false;
@@ -126,7 +128,8 @@ class Node {
 
   NodeConfig cfg_;
   ModelProvider* provider_;
-  cudaStream_t compute_ = nullptr, copy_ = nullptr;
+  cudaStream_t compute_ = nullptr, copy_ = nullptr;  // kernels / weight page-in
+  cudaStream_t in_ = nullptr, out_ = nullptr;         // request inputs H2D / results D2H
   char* slab_ = nullptr;
   Arena arena_;
 
@@ -150,7 +153,8 @@ class Node {
   std::mutex q_mu_;
   std::condition_variable q_cv_, slot_cv_;
   std::unordered_map<DeviceModel*, std::deque<PredictRequest*>> pending_;
-  std::deque<DeviceModel*> order_;
+  std::set<std::pair<uint64_t, DeviceModel*>> order_;  // (seq of the model's oldest request, model)
+  uint64_t seq_ = 0;
   std::deque<Slot*> inflight_;
   std::vector<Slot> slots_;
   std::thread batcher_, completer_;
