@@ -198,6 +198,10 @@ int tfsc_k_affine(const float* x, float* y, int64_t n, const float* a, const flo
 int tfsc_k_dense(const float* x, const float* w, const float* b, float* y, int rows, int k, int n, int relu,
                  float* workspace, size_t workspace_bytes, void* stream);                                    /* X2 */
 size_t tfsc_k_dense_workspace(int rows, int k, int n);
+/* X3: the tcgen05/TMEM (3xTF32) path alone, rows <= 64, n % 32 == 0, k % 4 == 0. tfsc_k_dense picks it
+ * automatically for more than 8 rows; this entry exists for parity tests and roofline timing. */
+int tfsc_k_dense_tc(const float* x, const float* w, const float* b, float* y, int rows, int k, int n, int relu,
+                    float* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,11 +7,13 @@
 #include "kernels.h"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace tfsc {
 
 static std::atomic<int64_t> g_launches{0};
-int64_t kernel_launch_count() { return g_launches.load(); }
+extern std::atomic<int64_t> g_launches_tc;
+int64_t kernel_launch_count() { return g_launches.load() + g_launches_tc.load(); }
 
 // ------------------------------------------------------------------------------------ X1 ----
 __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n,
@@ -251,12 +253,25 @@ static DensePlan plan_dense(int k, int n) {
   return p;
 }
 
-size_t dense_workspace_bytes(int rows, int k, int n) {
-  (void)rows;
+static size_t stream_workspace_bytes(int k, int n) {
   DensePlan p = plan_dense(k, n);
   size_t counters = ((size_t)p.strips * sizeof(unsigned int) + 255) & ~(size_t)255;
   size_t partials = (size_t)p.strips * p.splits * kMaxRowsPerLaunch * kStripCols * sizeof(float);
   return counters + partials;
+}
+
+size_t dense_workspace_bytes(int rows, int k, int n) {
+  (void)rows;
+  size_t a = stream_workspace_bytes(k, n), b = dense_tc_workspace_bytes(k, n);
+  return a > b ? a : b;
+}
+
+static int tc_min_rows() {  // rows per group from which the tensor-core path is used (0 = never)
+  static int v = [] {
+    const char* e = getenv("TFSC_TC_MIN_ROWS");
+    return e ? atoi(e) : 9;
+  }();
+  return v;
 }
 
 template <int R>
@@ -297,7 +312,18 @@ cudaError_t launch_dense(const float* x, const float* w, const float* bias, floa
     return cudaGetLastError();
   }
   const DensePlan p = plan_dense(k, n);
-  for (int r0 = 0; r0 < rows; r0 += kMaxRowsPerLaunch) {
+  int r_done = 0;
+  if (tc_min_rows() > 0 && rows >= tc_min_rows() && dense_tc_supported(rows > 64 ? 64 : rows, k, n, w, x, bias, y)) {
+    // batches of more than 8 rows: one tensor-core pass per 64 rows instead of ceil(rows/8) SIMT passes
+    while (rows - r_done >= tc_min_rows()) {
+      const int rr = rows - r_done < 64 ? rows - r_done : 64;
+      cudaError_t e = launch_dense_tc(x + (size_t)r_done * k, w, bias, y + (size_t)r_done * n, rr, k, n, relu, workspace,
+                                      workspace_bytes, s);
+      if (e != cudaSuccess) return e;
+      r_done += rr;
+    }
+  }
+  for (int r0 = r_done; r0 < rows; r0 += kMaxRowsPerLaunch) {
     const int rr = rows - r0 < kMaxRowsPerLaunch ? rows - r0 : kMaxRowsPerLaunch;
     const float* xp = x + (size_t)r0 * k;
     float* yp = y + (size_t)r0 * n;

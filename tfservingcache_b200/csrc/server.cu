@@ -634,4 +634,13 @@ int tfsc_k_dense(const float* x, const float* w, const float* b, float* y, int r
 
 size_t tfsc_k_dense_workspace(int rows, int k, int n) { return dense_workspace_bytes(rows, k, n); }
 
+int tfsc_k_dense_tc(const float* x, const float* w, const float* b, float* y, int rows, int k, int n, int relu,
+                    float* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_device()) return rc;
+  if (!dense_tc_supported(rows, k, n, w, x, b, y))
+    return fail(TFSC_E_INVALID, "dense_tc: unsupported shape/alignment (rows<=64, n%%32==0, k%%4==0, 16B-aligned)");
+  cudaError_t e = launch_dense_tc(x, w, b, y, rows, k, n, relu != 0, workspace, workspace_bytes, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "dense_tc: %s", cudaGetErrorString(e));
+}
+
 }  // extern "C"
