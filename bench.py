@@ -100,18 +100,31 @@ def step_groups(wl, rank, step, tick_global):
     return mine, [(m, counts[m]) for m in order]
 
 
+def pass_plan(rows, tc_min=9):
+    """Mirror of launch_dense (csrc/kernels.cu): groups of >= 9 rows take the tcgen05 path, 64 rows per
+    pass; what is left (<= 8 rows) takes one SIMT streaming pass."""
+    out, r = [], rows
+    while tc_min > 0 and r >= tc_min:
+        rr = min(64, r)
+        out.append(("tc", rr))
+        r -= rr
+    while r > 0:
+        rr = min(8, r)
+        out.append(("simt", rr))
+        r -= rr
+    return out
+
+
 def algorithmic_bytes(groups, dims):
-    """per launch of one dense layer = W + bias + rows*(in+out)*4; rows > 8 are run as
-    ceil(rows/8) passes, each streaming W once."""
-    total, launches = 0, 0
+    """per launch of one dense layer = W + bias + rows*(in+out)*4; every pass streams W once."""
+    total, launches, tc = 0, 0, 0
+    tc_min = int(os.environ.get("TFSC_TC_MIN_ROWS", "9"))
     for _m, rows in groups:
-        r = rows
-        while r > 0:
-            rr = min(8, r)
+        for kind, rr in pass_plan(rows, tc_min):
             for l in range(len(dims) - 1):
                 total += dims[l] * dims[l + 1] * 4 + dims[l + 1] * 4 + rr * (dims[l] + dims[l + 1]) * 4
                 launches += 1
-            r -= rr
+                tc += kind == "tc"
     return total, launches
 
 
@@ -196,7 +209,7 @@ def run_b200(args):
     cfg = {"modelProvider.type": "synthetic", "modelProvider.synthetic.dims": dims,
            "modelProvider.synthetic.count": wl["n_models"], "modelProvider.synthetic.namePrefix": "m",
            "modelProvider.synthetic.threads": max(4, min(32, (os.cpu_count() or 8) // max(world, 1))),
-           "gpu.devices": [local], "gpu.arenaBytes": arena, "gpu.maxBatch": 8, "gpu.maxRequestRows": 4096,
+           "gpu.devices": [local], "gpu.arenaBytes": arena, "gpu.maxBatch": 64, "gpu.maxRequestRows": 4096,
            "gpu.stagingSlots": 4, "modelCache.size": int(host_gib * 2**30), "serving.maxConcurrentModels": 1 << 20,
            "proxy.replicasPerModel": wl["replicas"], "gpu.members": wl["members"], "gpu.localMembers": [wl["members"][rank]],
            "proxy.seed": 1}
@@ -322,7 +335,7 @@ def run_b200(args):
             "config": {"workload": f"BASELINE configs[2] per-GPU shard: {args.models_per_gpu} per-tenant 3-layer MLP "
                                    f"({'x'.join(map(str, dims))} fp32, {model_bytes} B) per GPU, Zipf alpha=1.0, ring replicas={wl['replicas']}; "
                                    f"at 8 GPUs = configs[2] (1000 models)",
-                       "models_total": wl["n_models"], "tick_requests_per_gpu": args.tick, "max_rows_per_pass": 8,
+                       "models_total": wl["n_models"], "tick_requests_per_gpu": args.tick, "max_rows_per_pass": "8 (SIMT) / 64 (tcgen05 3xTF32)",
                        "l2": "inputs larger than L2 (>=1 GB of weights streamed per model pass); L2 flushed before timing",
                        "arena_gib": round(arena / 2**30, 1), "host_tier_gib": round(host_gib, 1), "cold_load_s": round(load_s, 1)},
             "e2e": {"value": round(e2e_val, 1), "unit": "req/s",
@@ -335,7 +348,7 @@ def run_b200(args):
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "kernel": "dense_stream_kernel<R> (fused xW+b+ReLU, split-K)", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "dense_stream_kernel<R> (<=8 rows) + dense_tc_kernel<RP> (9..64 rows, tcgen05 3xTF32): fused xW+b+ReLU, split-K", "peak_source": peak_src,
                          "launches_timed": n_dense, "avg_launch_us": round(elapsed_ms * 1e3 / max(1, n_dense), 2)},
         }
         if cpu_base:

@@ -27,6 +27,14 @@ namespace tfsc {
 extern std::atomic<int64_t> g_launches_tc;
 std::atomic<int64_t> g_launches_tc{0};
 
+// Optional timeline trace of CTA (0,0) (debug builds only: -DTFSC_TC_TRACE): clock64 stamps per k-block
+#ifdef TFSC_TC_TRACE
+__device__ long long g_tc_trace[8][128];
+#define TC_TRACE(slot, kb) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (kb) < 128) g_tc_trace[slot][kb] = clock64(); } while (0)
+#else
+#define TC_TRACE(slot, kb) do {} while (0)
+#endif
+
 namespace tc {
 constexpr int BK = 32;                     // k rows per stage = one 128-byte swizzle row of tf32
 constexpr int TILE_M = 128;                // output columns per MMA
@@ -108,16 +116,53 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-// smem layout (dynamic, 1024-aligned): per stage [W_hi 32K][W_lo 32K][B' 2*RP*128], then barriers
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+// idesc for the TMEM-A MMA: A K-major (A from TMEM cannot be transposed), B K-major
+__host__ __device__ constexpr uint32_t make_idesc_ts(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// smem (dynamic, 1024-aligned): NS stages of W (32 KB each, TMA target, read by MMA1 and by the
+// converters), 2 buffers of B' = [x_hi ; x_lo] (2*RP rows x 128 B), then the mbarriers.
+// TMEM (512 columns): D tile t at columns [t*2RP, (t+1)*2RP): [0,RP) = W_hi.x_hi (main accumulator),
+// [RP,2RP) = W_hi.x_lo + W_lo.x_hi (small terms kept apart from the big one: the tensor core's fp32
+// accumulation truncates, so small terms must not be added into the large running sum);
+// W_lo operand buffers at columns [256 + cb*64 + t*32, +32), cb = k-block parity.
 template <int RP>
 struct TcSmem {
+  static constexpr int NS = 6;
   static constexpr int B_BYTES = 2 * RP * 128;
-  static constexpr int STAGE_BYTES = 2 * tc::W_BYTES + B_BYTES;
-  static constexpr int STAGES = (RP <= 32) ? 3 : 2;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;
+  static constexpr int W_TOTAL = NS * tc::W_BYTES;
+  static constexpr int TOTAL = W_TOTAL + 2 * B_BYTES + 256 + 1024;
 };
+constexpr uint32_t kAloCol = 256;
 
 template <int RP>
 __global__ void __launch_bounds__(tc::THREADS, 1)
@@ -125,30 +170,34 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap wmap, const float* __restric
                 float* __restrict__ y, int rows, int K, int N, int relu, int splits, int chunk_k,
                 unsigned int* __restrict__ counters, float* __restrict__ partials) {
   using S = TcSmem<RP>;
-  constexpr int STAGES = S::STAGES;
+  constexpr int NS = S::NS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
-  uint64_t* full = bars;                 // TMA landed W_hi
-  uint64_t* conv = bars + STAGES;        // converters done (W_lo, B')
-  uint64_t* empty = bars + 2 * STAGES;   // MMAs finished reading the stage
-  uint64_t* accum_full = bars + 3 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  uint8_t* bprime = smem + S::W_TOTAL;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bprime + 2 * S::B_BYTES);
+  uint64_t* full = bars;             // [NS] TMA landed the W stage
+  uint64_t* empty = bars + NS;       // [NS] MMAs finished reading the W stage
+  uint64_t* cfull = bars + 2 * NS;   // [2]  converters published B'[cb] and W_lo[cb]
+  uint64_t* cempty = cfull + 2;      // [2]  MMAs finished reading B'[cb] / W_lo[cb]
+  uint64_t* accum_full = cempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip = blockIdx.x, split = blockIdx.y;
   const int k_begin = split * chunk_k;
   const int k_end = min(K, k_begin + chunk_k);
   const int n_kblocks = (max(0, k_end - k_begin) + tc::BK - 1) / tc::BK;
-  constexpr int TMEM_COLS = (tc::TILES * 2 * RP <= 32) ? 32 : (tc::TILES * 2 * RP <= 64) ? 64
-                            : (tc::TILES * 2 * RP <= 128) ? 128 : (tc::TILES * 2 * RP <= 256) ? 256 : 512;
+  constexpr int TMEM_COLS = 512;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) {
+      for (int s = 0; s < NS; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&conv[s], tc::NUM_CONV_WARPS);
         mbar_init(&empty[s], 1);
+      }
+      for (int c = 0; c < 2; ++c) {
+        mbar_init(&cfull[c], tc::NUM_CONV_WARPS);
+        mbar_init(&cempty[c], 1);
       }
       mbar_init(accum_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -164,64 +213,72 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap wmap, const float* __restric
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: keeps NS x 32 KB of W in flight =====================
     for (int kb = 0; kb < n_kblocks; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
+      const int s = kb % NS, it = kb / NS;
       if (lane == 0) {
         if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        TC_TRACE(0, kb);
         mbar_expect_tx(&full[s], tc::W_BYTES);
-        tma_load_3d(smem + s * S::STAGE_BYTES, &wmap, &full[s], 0, k_begin + kb * tc::BK, strip * tc::SLABS);
+        // 8 boxes of {32 n, 4 k, 8 slabs}: every box covers 4 W rows x 1 KB contiguous, so the 128-byte
+        // pieces of one DRAM row are requested close together; smem stage = [k/4][slab][k%4][32 n]
+#pragma unroll
+        for (int g = 0; g < tc::BK / 4; ++g)
+          tma_load_3d(smem + s * tc::W_BYTES + g * 4096, &wmap, &full[s], 0, k_begin + kb * tc::BK + g * 4, strip * tc::SLABS);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc1 = make_idesc(2 * RP);
-    constexpr uint32_t idesc2 = make_idesc(RP);
+    constexpr uint32_t idesc1 = make_idesc(2 * RP);   // W_hi (smem, MN-major) x [x_hi ; x_lo]
+    constexpr uint32_t idesc2 = make_idesc_ts(RP);    // W_lo (TMEM)           x  x_hi
     for (int kb = 0; kb < n_kblocks; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
+      const int s = kb % NS, cb = kb & 1, cit = kb >> 1;
       if (lane == 0) {
-        mbar_wait(&conv[s], it & 1);
+        mbar_wait(&cfull[cb], cit & 1);  // converters waited on full[s] themselves
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t whi = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint32_t wlo = whi + tc::W_BYTES;
-        const uint32_t bp = wlo + tc::W_BYTES;
+        TC_TRACE(1, kb);
+        const uint32_t whi = smem_u32(smem + s * tc::W_BYTES);
+        const uint32_t bp = smem_u32(bprime + cb * S::B_BYTES);
 #pragma unroll
         for (int t = 0; t < tc::TILES; ++t) {
           const uint32_t d = tmem_base + (uint32_t)(t * 2 * RP);
+          const uint32_t alo = tmem_base + kAloCol + (uint32_t)(cb * 64 + t * 32);
 #pragma unroll
           for (int k8 = 0; k8 < tc::BK / 8; ++k8) {
-            // A (MN-major tf32, SWIZZLE_128B_BASE32B): 4 slabs of 32 columns at LBO = 4 KB, 4-row k groups
-            // at SBO = 512 B (rows are 128 B = 32 columns wide)
-            const uint64_t a_hi = make_desc(whi + t * 4 * tc::SLAB_BYTES + k8 * 1024, tc::SLAB_BYTES, 512, 1);
-            const uint64_t a_lo = make_desc(wlo + t * 4 * tc::SLAB_BYTES + k8 * 1024, tc::SLAB_BYTES, 512, 1);
+            // A (MN-major tf32, SWIZZLE_128B_BASE32B): atoms of 4 k-rows x 128 B (32 columns); the 4 slabs
+            // of a tile sit LBO = 512 B apart, consecutive 4-row k groups SBO = 4 KB apart
+            const uint64_t a_hi = make_desc(whi + t * 4 * 512 + k8 * 8192, 512, 4096, 1);
             // B' (K-major, SWIZZLE_128B): 8-row groups at SBO = 1 KB, k advances 32 B inside the swizzle row
             const uint64_t b = make_desc(bp + k8 * 32, 16, 1024, 2);
             umma_tf32_ss(d, a_hi, b, idesc1, (kb | k8) ? 1u : 0u);
-            umma_tf32_ss(d, a_lo, b, idesc2, 1u);
+            umma_tf32_ts(d + RP, alo + k8 * 8, b, idesc2, 1u);
           }
         }
         umma_commit(&empty[s]);
+        umma_commit(&cempty[cb]);
+        TC_TRACE(2, kb);
       }
       __syncwarp();
     }
     if (lane == 0) umma_commit(accum_full);
     __syncwarp();
   } else {
-    // ===================== converters: W_lo and B' = [x_hi ; x_lo] =====================
+    // ===================== converters: B' = [x_hi ; x_lo] (smem) and W_lo (TMEM) =====================
     const int ct = threadIdx.x - 64;  // 0..255
-    for (int kb = 0; kb < n_kblocks; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
-      uint8_t* stage = smem + s * S::STAGE_BYTES;
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int t = (warp - 2) >> 2;    // tile 0 for warps 2..5, tile 1 for warps 6..9
+    constexpr int XI = (RP * 8 + 255) / 256;  // x items (float4) per thread per k-block
+    float4 xr[2][XI];                         // register ring: x is fetched two k-blocks ahead (L2 latency)
+    auto load_x = [&](int kb, float4* dst) {
       const int k0 = k_begin + kb * tc::BK;
-      // B' first (needs only global x): 2 slots (hi, lo) per (row, 16-byte chunk)
-      if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
-      float4* bp = reinterpret_cast<float4*>(stage + 2 * tc::W_BYTES);
-      for (int idx = ct; idx < RP * 8; idx += tc::NUM_CONV_WARPS * 32) {
+#pragma unroll
+      for (int j = 0; j < XI; ++j) {
+        const int idx = ct + j * 256;
         const int r = idx >> 3, c = idx & 7;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         const int kk = k0 + c * 4;
-        if (r < rows) {
+        if (idx < RP * 8 && r < rows) {
           const float* src = x + (size_t)r * K + kk;
           if (kk + 3 < k_end) v = __ldg(reinterpret_cast<const float4*>(src));
           else {
@@ -230,40 +287,66 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap wmap, const float* __restric
             if (kk + 2 < k_end) v.z = __ldg(src + 2);
           }
         }
-        const float4 lo = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-        const int rl = r + RP;
-        bp[(r >> 3) * 64 + (r & 7) * 8 + (c ^ (r & 7))] = v;
-        bp[(rl >> 3) * 64 + (rl & 7) * 8 + (c ^ (rl & 7))] = lo;
+        dst[j] = v;
       }
-      // W_lo = W - trunc_tf32(W), elementwise in the layout TMA produced
-      mbar_wait(&full[s], it & 1);
-      const float4* whi = reinterpret_cast<const float4*>(stage);
-      float4* wlo = reinterpret_cast<float4*>(stage + tc::W_BYTES);
+    };
+    if (n_kblocks > 0) load_x(0, xr[0]);
+    if (n_kblocks > 1) load_x(1, xr[1]);
+    // shared address of this thread's column inside a W stage, before the per-row swizzle
+    const uint32_t w_col_base = smem_u32(smem) + (uint32_t)((t * 4 + q) * 512 + (lane & 7) * 4);
+    const uint32_t bp_base = smem_u32(bprime);
+    auto body = [&](int kb, float4* xcur) {
+      const int s = kb % NS, it = kb / NS, cb = kb & 1, cit = kb >> 1;
+      if (ct == 0) TC_TRACE(3, kb);
+      if (cit > 0) mbar_wait(&cempty[cb], (cit - 1) & 1);
+      if (ct == 0) TC_TRACE(4, kb);
+      const uint32_t bp = bp_base + cb * S::B_BYTES;
 #pragma unroll
-      for (int i = 0; i < tc::W_BYTES / 16 / (tc::NUM_CONV_WARPS * 32); ++i) {
-        const float4 v = whi[ct + i * tc::NUM_CONV_WARPS * 32];
-        wlo[ct + i * tc::NUM_CONV_WARPS * 32] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+      for (int j = 0; j < XI; ++j) {
+        const int idx = ct + j * 256;
+        if (idx < RP * 8) {
+          const int r = idx >> 3, c = idx & 7, rl = r + RP;
+          const float4 v = xcur[j];
+          sts_f4(bp + (uint32_t)(((r >> 3) * 64 + (r & 7) * 8 + (c ^ (r & 7))) * 16), v);
+          sts_f4(bp + (uint32_t)(((rl >> 3) * 64 + (rl & 7) * 8 + (c ^ (rl & 7))) * 16),
+                 make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)));
+        }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+      if (kb + 2 < n_kblocks) load_x(kb + 2, xcur);
+      // W_lo[m][k] = W[k][m] - trunc_tf32(W[k][m]) -> TMEM (lane = output column m, column = k)
+      mbar_wait(&full[s], it & 1);
+      if (ct == 0) TC_TRACE(5, kb);
+      const uint32_t wst = w_col_base + (uint32_t)(s * tc::W_BYTES);
+      uint32_t lo[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        lo[k] = __float_as_uint(tf32_lo(lds_f32(wst + (k >> 2) * 4096 + (k & 3) * 128 + ((((lane >> 3) ^ (k & 3))) << 5))));
+      tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + kAloCol + (uint32_t)(cb * 64 + t * 32), lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // B' writes -> visible to the MMA (async proxy)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&conv[s]);
+      if (ct == 0) TC_TRACE(6, kb);
+      if (lane == 0) mbar_arrive(&cfull[cb]);
+    };
+    for (int kb = 0; kb < n_kblocks; kb += 2) {
+      body(kb, xr[0]);
+      if (kb + 1 < n_kblocks) body(kb + 1, xr[1]);
     }
     // ===================== epilogue: TMEM -> split-K partials =====================
     mbar_wait(accum_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int t = (warp - 2) >> 2;       // tile 0 for warps 2..5, tile 1 for warps 6..9
     const int ncol = t * tc::TILE_M + q * 32 + lane;  // column within the strip
     float* my_partial = partials + ((size_t)(strip * splits + split) * RP) * tc::STRIP;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 2 * RP);
     if (n_kblocks > 0) {
 #pragma unroll
       for (int c = 0; c < RP; c += 16) {
-        float hi[16], lo[16];
+        float hi[16], sm[16];
         tmem_ld16(taddr + c, hi);
-        tmem_ld16(taddr + RP + c, lo);
+        tmem_ld16(taddr + RP + c, sm);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) my_partial[(size_t)(c + i) * tc::STRIP + ncol] = hi[i] + lo[i];
+        for (int i = 0; i < 16; ++i) my_partial[(size_t)(c + i) * tc::STRIP + ncol] = hi[i] + sm[i];
       }
     } else {
       for (int r = 0; r < RP; ++r) my_partial[(size_t)r * tc::STRIP + ncol] = 0.f;
@@ -342,7 +425,7 @@ static bool get_wmap(const float* w, int k, int n, CUtensorMap* out) {
   CUtensorMap m;
   const cuuint64_t gdim[3] = {32, (cuuint64_t)k, (cuuint64_t)(n / 32)};
   const cuuint64_t gstride[2] = {(cuuint64_t)n * 4, 128};
-  const cuuint32_t box[3] = {32, (cuuint32_t)tc::BK, (cuuint32_t)tc::SLABS};
+  const cuuint32_t box[3] = {32, 4, (cuuint32_t)tc::SLABS};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -353,6 +436,12 @@ static bool get_wmap(const float* w, int k, int n, CUtensorMap* out) {
   *out = m;
   return true;
 }
+
+#ifdef TFSC_TC_TRACE
+extern "C" int tfsc_tc_trace_read(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 8 * 128) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 struct TcPlan {
   int strips, splits, chunk_k;
