@@ -222,8 +222,12 @@ def run_b200(args):
         srv.ensure(0, f"m{m}", 1)
     load_s = time.time() - t_load
 
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: handle 0 (the legacy default stream) means "the node's own compute
+    # stream" to tfsc_predict_device, and the CUDA events below must sit on the stream the kernels run on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
     max_rows = args.tick * 4
     x_dev = torch.randn(max_rows, in_dim, device="cuda", dtype=torch.float32)
     y_dev = torch.empty(max_rows, out_dim, device="cuda", dtype=torch.float32)
