@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident part alone")
     ap.add_argument("--dims", type=int, nargs="*", default=None, help="override model dims (debug only)")
+    ap.add_argument("--replica-pick", default="hot-spread", choices=["hot-spread", "random", "first"],
+                    help="replica choice among the ring's GetN candidates (reference: random)")
     return ap.parse_args()
 
 
@@ -66,7 +68,7 @@ def splitmix(i: np.ndarray) -> np.ndarray:
     return z ^ (z >> np.uint64(31))
 
 
-def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42):
+def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42, pick_policy="hot-spread"):
     """Global request stream + ring routing, identical on every rank (no communication)."""
     import tfservingcache_b200 as t
     from oracle.zipf import zipf_trace  # trace generator only (test/bench infrastructure)
@@ -81,10 +83,14 @@ def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42):
         owners[j] = [int(s.host[3:]) for s in nodes]
     total = tick * n_gpus * n_steps
     trace = zipf_trace(n_models, total, 1.0, seed)
-    # "Pick random node" (taskhandler.go:91) with a counter-based RNG so all ranks agree
-    pick = (splitmix(np.arange(total)) % np.uint64(replicas)).astype(np.int64)
+    # replica choice (taskhandler.go:91 picks at random; default here: primary unless the model is hot) with the
+    # library's deterministic picker, fed the same global request sequence on every rank so all ranks agree
+    picker = t.ReplicaPicker(pick_policy, seed, 0.5)
+    keys = [t.model_key(f"m{j}", "1") for j in range(n_models)]
+    pick = np.fromiter((picker.pick(keys[m], replicas, n_gpus) for m in trace.tolist()), dtype=np.int64, count=total)
     dest = owners[trace, pick]
-    return dict(n_models=n_models, replicas=replicas, members=members, trace=trace, dest=dest, owners=owners)
+    return dict(n_models=n_models, replicas=replicas, members=members, trace=trace, dest=dest, owners=owners,
+                pick_policy=pick_policy)
 
 
 def step_groups(wl, rank, step, tick_global):
@@ -192,7 +198,7 @@ def run_b200(args):
     W, K = args.warmup, args.steps
     e2e_steps = args.e2e_steps or K
     n_steps_total = W + K + W + e2e_steps
-    wl = build_workload(world, args.models_per_gpu, args.tick, n_steps_total)
+    wl = build_workload(world, args.models_per_gpu, args.tick, n_steps_total, pick_policy=args.replica_pick)
     tick_global = args.tick * world
 
     free_b, _tot = torch.cuda.mem_get_info()
@@ -211,8 +217,10 @@ def run_b200(args):
            "modelProvider.synthetic.threads": max(4, min(32, (os.cpu_count() or 8) // max(world, 1))),
            "gpu.devices": [local], "gpu.arenaBytes": arena, "gpu.maxBatch": 64, "gpu.maxRequestRows": 4096,
            "gpu.stagingSlots": 4, "modelCache.size": int(host_gib * 2**30), "serving.maxConcurrentModels": 1 << 20,
-           "proxy.replicasPerModel": wl["replicas"], "gpu.members": wl["members"], "gpu.localMembers": [wl["members"][rank]],
-           "proxy.seed": 1}
+           # routing is done above with the library's ring + picker over the GLOBAL member list; this rank's
+           # server only ever sees the requests it owns, so its own ring has a single member
+           "proxy.replicasPerModel": 1, "gpu.members": [wl["members"][rank]], "gpu.localMembers": [wl["members"][rank]],
+           "proxy.seed": 1, "proxy.replicaPick": "first"}
     srv = t.Server(cfg)
 
     # page every model this rank owns into HBM once (cold loads are not part of the steady-state metric;
@@ -337,7 +345,8 @@ def run_b200(args):
             "ms_per_step": round(elapsed_ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[2] per-GPU shard: {args.models_per_gpu} per-tenant 3-layer MLP "
-                                   f"({'x'.join(map(str, dims))} fp32, {model_bytes} B) per GPU, Zipf alpha=1.0, ring replicas={wl['replicas']}; "
+                                   f"({'x'.join(map(str, dims))} fp32, {model_bytes} B) per GPU, Zipf alpha=1.0, ring replicas={wl['replicas']} "
+                                   f"(replica pick: {wl['pick_policy']}); "
                                    f"at 8 GPUs = configs[2] (1000 models)",
                        "models_total": wl["n_models"], "tick_requests_per_gpu": args.tick, "max_rows_per_pass": "8 (SIMT) / 64 (tcgen05 3xTF32)",
                        "l2": "inputs larger than L2 (>=1 GB of weights streamed per model pass); L2 flushed before timing",

@@ -291,3 +291,25 @@ def test_config_yaml_and_env(tmp_path):
     assert cfg["serving.maxConcurrentModels"] == 32 and cfg["proxy.replicasPerModel"] == 2
     assert cfg["modelCache.size"] == 30000 and cfg["logging.level"] == "debug"
     assert cfg["healthprobe.modelName"] == "__TFSERVINGCACHE_PROBE_CHECK__"
+
+
+# ---- replica pick policies (taskhandler.go:91 is "random") --------------------------------------
+def test_replica_picker_policies():
+    import collections
+    first = t.ReplicaPicker("first", 1)
+    assert {first.pick("k", 3, 8) for _ in range(50)} == {0}
+    rnd = t.ReplicaPicker("random", 1)
+    c = collections.Counter(rnd.pick("k", 2, 8) for _ in range(2000))
+    assert 800 < c[0] < 1200 and set(c) == {0, 1}
+    # same seed + same call sequence -> same decisions (ranks agree without communicating)
+    a, b = t.ReplicaPicker("hot-spread", 42), t.ReplicaPicker("hot-spread", 42)
+    from oracle.zipf import zipf_trace
+    tr = zipf_trace(1000, 30000, 1.0, 42).tolist()
+    pa = [a.pick(f"m{m}##1", 2, 8) for m in tr]
+    assert pa == [b.pick(f"m{m}##1", 2, 8) for m in tr]
+    spread = {m for m, p in zip(tr, pa) if p == 1}
+    top = [m for m, _ in collections.Counter(tr).most_common(2)]
+    assert spread == set(top)          # only the models above 0.5/8 of the traffic leave their primary
+    with pytest.raises(ValueError):
+        t.ReplicaPicker("nope", 1)
+    assert t.ReplicaPicker("hot-spread", 3).pick("k", 1, 8) == 0

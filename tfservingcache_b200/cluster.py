@@ -68,6 +68,24 @@ class ClusterConnection:
         return lib.tfsc_ring_points(self._h)
 
 
+class ReplicaPicker:
+    """Replica choice among the GetN candidates: "random" (reference, taskhandler.go:91), "first",
+    "hot-spread" (primary unless the key is hot).  Deterministic for a given seed + call sequence."""
+
+    def __init__(self, policy: str = "random", seed: int = 0, hot_fraction: float = 0.5):
+        self._h = lib.tfsc_picker_new(policy.encode(), seed, hot_fraction)
+        if not self._h:
+            raise ValueError(lib.tfsc_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.tfsc_picker_free(self._h)
+            self._h = None
+
+    def pick(self, key: str, n_replicas: int, members: int) -> int:
+        return check(lib.tfsc_picker_pick(self._h, key.encode(), n_replicas, members), "picker_pick")
+
+
 class TaskHandler:
     """taskhandler.go:20-92: key = name + "##" + version, uniform random pick among replicas."""
 

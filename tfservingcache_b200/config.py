@@ -16,7 +16,7 @@ KNOWN_KEYS = [
     "serving.servingModelPath", "serving.grpcHost", "serving.restHost", "serving.maxConcurrentModels",
     "serving.grpcConfigTimeout", "serving.grpcPredictTimeout", "serving.grpcMaxMsgSize", "serving.metricsPath",
     "serving.modelFetchTimeout",
-    "proxy.replicasPerModel", "proxy.grpcTimeout", "proxy.replicaPick", "proxy.seed",
+    "proxy.replicasPerModel", "proxy.grpcTimeout", "proxy.replicaPick", "proxy.seed", "proxy.hotFraction",
     "logging.level", "logging.format", "healthprobe.modelName",
     "gpu.devices", "gpu.arenaBytes", "gpu.maxBatch", "gpu.maxRequestRows", "gpu.stagingSlots",
     "gpu.members", "gpu.localMembers",

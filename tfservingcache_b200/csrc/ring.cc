@@ -100,9 +100,41 @@ bool Ring::get_n(const std::string& key, int n, std::vector<std::string>* out) c
   return true;
 }
 
+ReplicaPicker::ReplicaPicker(const std::string& policy, uint64_t seed, double hot_fraction)
+    : policy_(policy), rng_(0x9E3779B97F4A7C15ull ^ (seed * 0xD1342543DE82EF95ull + 1)), hot_fraction_(hot_fraction) {}
+
+uint64_t ReplicaPicker::next() {  // xorshift64*
+  rng_ ^= rng_ >> 12;
+  rng_ ^= rng_ << 25;
+  rng_ ^= rng_ >> 27;
+  return rng_ * 0x2545F4914F6CDD1Dull;
+}
+
+int ReplicaPicker::pick(const std::string& key, int n_replicas, int members) {
+  if (n_replicas <= 1 || policy_ == "first") return 0;
+  if (policy_ == "random") return (int)(next() % (uint64_t)n_replicas);
+  // hot-spread: sliding-window request share, halved every 64 Ki requests
+  uint32_t& c = counts_[key];
+  ++c;
+  if (++window_ >= 65536) {
+    for (auto it = counts_.begin(); it != counts_.end();) {
+      it->second >>= 1;
+      if (it->second == 0) it = counts_.erase(it);
+      else ++it;
+    }
+    window_ >>= 1;
+  }
+  const bool hot = window_ >= 256 && (double)c * (double)(members > 0 ? members : 1) > hot_fraction_ * (double)window_;
+  return hot ? (int)(next() % (uint64_t)n_replicas) : 0;
+}
+
 }  // namespace tfsc
 
 using tfsc::Ring;
+struct tfsc_picker {
+  tfsc::ReplicaPicker p;
+  tfsc_picker(const char* policy, uint64_t seed, double hf) : p(policy, seed, hf) {}
+};
 struct tfsc_ring {
   Ring r;
 };
@@ -131,6 +163,19 @@ int tfsc_ring_getn(const tfsc_ring* r, const char* key, int n, char* buf, size_t
   }
   int rc = tfsc::copy_out(joined, buf, cap);
   return rc < 0 ? rc : (int)out.size();
+}
+tfsc_picker* tfsc_picker_new(const char* policy, uint64_t seed, double hot_fraction) {
+  std::string p = policy ? policy : "random";
+  if (p != "random" && p != "first" && p != "hot-spread") {
+    tfsc::fail(TFSC_E_INVALID, "unknown proxy.replicaPick '%s'", p.c_str());
+    return nullptr;
+  }
+  return new tfsc_picker(p.c_str(), seed, hot_fraction > 0 ? hot_fraction : 0.5);
+}
+void tfsc_picker_free(tfsc_picker* p) { delete p; }
+int tfsc_picker_pick(tfsc_picker* p, const char* key, int n_replicas, int members) {
+  if (!p || !key || n_replicas < 1) return tfsc::fail(TFSC_E_INVALID, "picker_pick: bad arguments");
+  return p->p.pick(key, n_replicas, members);
 }
 int tfsc_model_key(const char* model_name, const char* version, char* buf, size_t cap) {
   if (!model_name || !version) return tfsc::fail(TFSC_E_INVALID, "model_key: bad arguments");

@@ -32,4 +32,27 @@ class Ring {
   std::vector<const std::string*> sorted_member_;  // parallel to sorted_
 };
 
+// Replica choice among the GetN candidates (taskhandler.go:91 picks uniformly at random).
+//   "random"     the reference's policy: every model ends up cached on all k replicas.
+//   "first"      always the primary (ring order).
+//   "hot-spread" primary unless the key is hot: a key whose share of recent requests exceeds
+//                hot_fraction / members is spread uniformly over its replicas. Keeps one HBM copy of cold
+//                models (paging a 1 GB model over PCIe costs ~100x serving it) and k copies of the few hot
+//                ones. Deterministic given the seed and the request sequence, so independent processes
+//                that see the same stream agree without communicating.
+class ReplicaPicker {
+ public:
+  ReplicaPicker(const std::string& policy, uint64_t seed, double hot_fraction = 0.5);
+  int pick(const std::string& key, int n_replicas, int members);
+  const std::string& policy() const { return policy_; }
+
+ private:
+  uint64_t next();
+  std::string policy_;
+  uint64_t rng_;
+  double hot_fraction_;
+  std::map<std::string, uint32_t> counts_;
+  uint64_t window_ = 0;
+};
+
 }  // namespace tfsc

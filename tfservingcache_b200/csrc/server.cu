@@ -29,36 +29,30 @@ struct tfsc_server {
   Ring ring;
   std::map<std::string, int> member_node;
   int replicas = 1;
-  std::string pick_policy = "random";
-  std::mutex rng_mu;
-  uint64_t rng = 0x9E3779B97F4A7C15ull;
+  std::mutex pick_mu;
+  std::unique_ptr<ReplicaPicker> picker;
   std::atomic<int64_t> req_rest{0}, req_grpc{0}, fail_rest{0}, fail_grpc{0};
-
-  uint64_t next_rand() {  // xorshift64*
-    std::lock_guard<std::mutex> lk(rng_mu);
-    rng ^= rng >> 12;
-    rng ^= rng << 25;
-    rng ^= rng >> 27;
-    return rng * 0x2545F4914F6CDD1Dull;
-  }
 };
 
 static int route(tfsc_server* s, const std::string& name, const std::string& version, std::vector<int>* nodes,
                  int* picked) {
   std::vector<std::string> members;
+  const std::string key = name + "##" + version;
+  int n_members = 0;
   {
     std::lock_guard<std::mutex> lk(s->ring_mu);
     // FindNodeForKey: GetN(key, max(replicasPerModel, 1)), cluster.go:117
-    if (!s->ring.get_n(name + "##" + version, s->replicas < 1 ? 1 : s->replicas, &members))
-      return fail(TFSC_E_EMPTY_RING, "empty circle");
+    if (!s->ring.get_n(key, s->replicas < 1 ? 1 : s->replicas, &members)) return fail(TFSC_E_EMPTY_RING, "empty circle");
+    n_members = s->ring.members();
     nodes->clear();
     for (auto& m : members) {
       auto it = s->member_node.find(m);
       nodes->push_back(it == s->member_node.end() ? -1 : it->second);
     }
   }
-  // "Pick random node", taskhandler.go:91 (uniform over the replica list)
-  *picked = s->pick_policy == "first" ? 0 : (int)(s->next_rand() % nodes->size());
+  // "Pick random node", taskhandler.go:91 (policy "random"), or the primary / hot-spread variants
+  std::lock_guard<std::mutex> lk(s->pick_mu);
+  *picked = s->picker->pick(key, (int)nodes->size(), n_members);
   return (int)nodes->size();
 }
 
@@ -110,11 +104,16 @@ tfsc_server* tfsc_server_create(const char* config_json) {
     }
   }
   s->replicas = (int)std::max(s->cfg.get_num("proxy.replicasPerModel", 1), 1.0);
-  s->pick_policy = s->cfg.get_str("proxy.replicaPick", "random");
+  const std::string policy = s->cfg.get_str("proxy.replicaPick", "random");
+  if (policy != "random" && policy != "first" && policy != "hot-spread") {
+    fail(TFSC_E_INVALID, "unknown proxy.replicaPick '%s'", policy.c_str());
+    return nullptr;
+  }
   int64_t seed = s->cfg.get_int("proxy.seed", -1);
   // rand.Seed(time.Now().UnixNano()), taskhandler.go:49, unless pinned for reproducible tests
-  s->rng ^= seed >= 0 ? (uint64_t)seed * 0x9E3779B97F4A7C15ull + 1
-                      : (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count();
+  s->picker = std::make_unique<ReplicaPicker>(
+      policy, seed >= 0 ? (uint64_t)seed : (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count(),
+      s->cfg.get_num("proxy.hotFraction", 0.5));
   if (const Json* lm = s->cfg.get("gpu.localMembers"))
     for (auto& v : lm->arr) s->local_members.push_back(v.string());
   for (size_t i = 0; i < devices.size(); ++i) {
