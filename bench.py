@@ -85,7 +85,7 @@ def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42, pick_policy="
     trace = zipf_trace(n_models, total, 1.0, seed)
     # replica choice (taskhandler.go:91 picks at random; default here: primary unless the model is hot) with the
     # library's deterministic picker, fed the same global request sequence on every rank so all ranks agree
-    picker = t.ReplicaPicker(pick_policy, seed, 0.5)
+    picker = t.ReplicaPicker(pick_policy, seed, 0.25)
     keys = [t.model_key(f"m{j}", "1") for j in range(n_models)]
     pick = np.fromiter((picker.pick(keys[m], replicas, n_gpus) for m in trace.tolist()), dtype=np.int64, count=total)
     dest = owners[trace, pick]
@@ -319,6 +319,7 @@ def run_b200(args):
         cc = torch.tensor([n_req, n_e2e, launches, alg_bytes, failed, n_dense], device="cuda", dtype=torch.float64)
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
         n_req_all, n_e2e_all, launches_all, failed_all = int(cc[0]), int(cc[1]), int(cc[2]), int(cc[4])
+        alg_bytes, n_dense = float(cc[3]) / world, int(cc[5])  # per-GPU average bytes over the max-over-ranks time
     else:
         n_req_all, n_e2e_all, launches_all, failed_all = n_req, n_e2e, launches, failed
 
@@ -362,7 +363,8 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "kernel": "dense_stream_kernel<R> (<=8 rows) + dense_tc_kernel<RP> (9..64 rows, tcgen05 3xTF32): fused xW+b+ReLU, split-K", "peak_source": peak_src,
-                         "launches_timed": n_dense, "avg_launch_us": round(elapsed_ms * 1e3 / max(1, n_dense), 2)},
+                         "launches_timed": n_dense, "avg_launch_us": round(elapsed_ms * 1e3 * world / max(1, n_dense), 2),
+                         "note": "per-GPU average algorithmic bytes / max-over-ranks device time"},
         }
         if cpu_base:
             line["cpu_baseline"] = cpu_base

@@ -134,6 +134,19 @@ tfsc_server* tfsc_server_create(const char* config_json) {
     s->nodes.push_back(std::move(node));
     if (s->local_members.size() <= i) s->local_members.push_back("gpu" + std::to_string(devices[i]) + ":0:0");
   }
+  // a6, the forward hop: every local GPU may read/write every other local GPU's memory over NVLink, so a
+  // request tensor that sits on GPU i is consumed by the owner GPU j's kernels in place (peer loads/stores)
+  for (int a : devices)
+    for (int b : devices) {
+      if (a == b) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
+        DeviceGuard g(a);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(b, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      }
+    }
   std::vector<std::string> members;
   if (const Json* m = s->cfg.get("gpu.members"))
     for (auto& v : m->arr) members.push_back(v.string());
