@@ -280,11 +280,13 @@ static cudaError_t launch_dense_r(const float* x, const float* w, const float* b
   size_t xs_bytes = (size_t)p.chunk_k * R * sizeof(float);
   size_t red_bytes = (size_t)kKLanes * R * kStripCols * sizeof(float);
   size_t smem = xs_bytes > red_bytes ? xs_bytes : red_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(dense_stream_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   unsigned int* counters = static_cast<unsigned int*>(workspace);
   size_t coff = ((size_t)p.strips * sizeof(unsigned int) + 255) & ~(size_t)255;
