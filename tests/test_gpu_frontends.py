@@ -1,0 +1,90 @@
+"""-m gpu: the REST + gRPC front-ends over real sockets (the reference's tfservingproxy_test.go scenarios with a
+real executor behind them instead of mocks)."""
+import json
+import threading
+import urllib.error
+import urllib.request
+
+import numpy as np
+import pytest
+
+import tfservingcache_b200 as t
+from oracle import models, wire
+from tfservingcache_b200 import serve
+
+pytestmark = pytest.mark.gpu
+DIMS = [64, 96, 8]
+
+
+@pytest.fixture(scope="module")
+def endpoints():
+    import torch
+    assert torch.cuda.is_available()
+    cfg = {"modelProvider.type": "synthetic", "modelProvider.synthetic.dims": DIMS, "modelProvider.synthetic.count": 16,
+           "gpu.devices": [0], "gpu.arenaBytes": 8 << 20, "serving.maxConcurrentModels": 4, "modelCache.size": 1 << 28}
+    srv = t.Server(cfg)
+    rest = serve.make_rest_server(srv, 0, "127.0.0.1")
+    g = serve.make_grpc_server(srv, 0, host="127.0.0.1")
+    g.start()
+    th = threading.Thread(target=rest.serve_forever, daemon=True)
+    th.start()
+    yield srv, f"http://127.0.0.1:{rest.server_port}", f"127.0.0.1:{g.bound_port}"
+    rest.shutdown()
+    g.stop(0)
+    srv.close()
+
+
+def _ref(j, x):
+    man, blob = models.synth_mlp_blob(DIMS, seed=1000 + j)
+    return models.forward(man, blob, np.asarray(x, np.float32), np.float64)
+
+
+def _http(url, body=None):
+    req = urllib.request.Request(url, data=body, method="POST" if body is not None else "GET")
+    try:
+        with urllib.request.urlopen(req, timeout=30) as r:
+            return r.status, r.read()
+    except urllib.error.HTTPError as e:
+        return e.code, e.read()
+
+
+def test_http_proxy_parses_url_and_predicts(endpoints):
+    _srv, base, _ = endpoints
+    x = np.random.default_rng(0).standard_normal((2, DIMS[0])).astype(np.float32)
+    st, body = _http(f"{base}/v1/models/m3/versions/1:predict", json.dumps({"instances": x.tolist()}).encode())
+    assert st == 200
+    y = np.array(json.loads(body)["predictions"])
+    assert y.shape == (2, DIMS[-1]) and np.max(np.abs(y - _ref(3, x))) <= 1e-4
+    st, body = _http(f"{base}/v1/models/m3/versions/1")
+    assert st == 200 and json.loads(body)["model_version_status"][0]["state"] == "AVAILABLE"
+
+
+def test_http_proxy_invalid_url_causes_404_and_missing_version_400(endpoints):
+    _srv, base, _ = endpoints
+    assert _http(f"{base}/v1/thisisabadrequest/foobar/versions/42") == (404, b'{"Status":"Error","Message":"Not found"}\n')
+    assert _http(f"{base}/v1/models/foobar") == (400, b'{"Status":"Error","Message":"Model version must be provided"}\n')
+    assert _http(f"{base}/v1/models/unknown/versions/1:predict", b'{"instances": [[1.0]]}')[0] == 404
+
+
+def test_grpc_proxy_predict_and_errors(endpoints):
+    import grpc
+    srv, _, target = endpoints
+    ch = grpc.insecure_channel(target)
+    predict = ch.unary_unary("/tensorflow.serving.PredictionService/Predict", request_serializer=lambda b: b,
+                             response_deserializer=lambda b: b)
+    x = np.random.default_rng(1).standard_normal((5, DIMS[0])).astype(np.float32)
+    spec, outs = wire.decode_predict_response(predict(wire.encode_predict_request("m7", 1, {"x": x})))
+    assert spec[:2] == ("m7", 1) and np.max(np.abs(outs["y"] - _ref(7, x))) <= 1e-4
+    with pytest.raises(grpc.RpcError) as e:
+        predict(wire.encode_predict_request("nope", 1, {"x": x}))
+    assert e.value.code() == grpc.StatusCode.NOT_FOUND
+    multi = ch.unary_unary("/tensorflow.serving.PredictionService/MultiInference", request_serializer=lambda b: b,
+                           response_deserializer=lambda b: b)
+    with pytest.raises(grpc.RpcError) as e:
+        multi(b"")
+    assert e.value.code() == grpc.StatusCode.UNIMPLEMENTED and "MultiInference not supported" in e.value.details()
+    health = ch.unary_unary("/grpc.health.v1.Health/Check", request_serializer=lambda b: b, response_deserializer=lambda b: b)
+    assert health(b"") == b"\x08\x01"
+    st = srv.stats()
+    assert st["proxy_requests_grpc"] >= 2 and st["proxy_failures_grpc"] >= 1
+    ch.close()

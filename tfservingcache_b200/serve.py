@@ -1,0 +1,111 @@
+"""Network front-ends of the cache tier (cmd/taskhandler/main.go:45-64): TF-Serving-compatible REST on
+`cacheRestPort` and gRPC on `cacheGrpcPort`, both thin shims over the C ABI -- the request bytes go straight to
+tfsc_rest_handle / tfsc_grpc_predict (libtfsc_b200.so does parsing, routing, residency, batching, execution).
+
+    python -m tfservingcache_b200.serve [config.yaml]
+
+gRPC is served with generic handlers and identity (de)serializers, so no generated stubs are needed and the
+PredictRequest is never re-marshalled (the reference unmarshals + re-marshals it at each of its two tiers).
+"""
+from __future__ import annotations
+
+import sys
+import threading
+from concurrent import futures
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+
+from . import _lib
+from .config import load_config
+from .server import Server
+
+_GRPC_CODE = {_lib.E_INVALID: "INVALID_ARGUMENT", _lib.E_TIMEOUT: "DEADLINE_EXCEEDED", _lib.E_NOT_FOUND: "NOT_FOUND",
+              _lib.E_EXHAUSTED: "RESOURCE_EXHAUSTED", _lib.E_UNIMPLEMENTED: "UNIMPLEMENTED", _lib.E_INTERNAL: "INTERNAL",
+              _lib.E_NO_DEVICE: "UNAVAILABLE", _lib.E_EMPTY_RING: "UNAVAILABLE", _lib.E_BUFFER: "INTERNAL"}
+
+
+def make_rest_server(srv: Server, port: int, host: str = "0.0.0.0") -> ThreadingHTTPServer:
+    class Handler(BaseHTTPRequestHandler):
+        protocol_version = "HTTP/1.1"
+
+        def _serve(self):
+            n = int(self.headers.get("Content-Length") or 0)
+            body = self.rfile.read(n) if n else b""
+            status, out = srv.rest_handle(self.command, self.path, body)   # RestProxy.Serve, tfservingproxy.go:93-129
+            self.send_response(status)
+            self.send_header("Content-Type", "application/json")
+            self.send_header("Content-Length", str(len(out)))
+            self.end_headers()
+            self.wfile.write(out)
+
+        do_GET = do_POST = _serve
+
+        def log_message(self, *a):
+            pass
+
+    httpd = ThreadingHTTPServer((host, port), Handler)
+    httpd.daemon_threads = True
+    return httpd
+
+
+def make_grpc_server(srv: Server, port: int, max_msg: int = 16 * 1024 * 1024, workers: int = 64, host: str = "0.0.0.0"):
+    import grpc
+
+    ident = lambda b: b  # noqa: E731
+
+    def predict(request: bytes, context):
+        try:
+            return srv.grpc_predict(request)       # proxyServiceServer.Predict, tfservingproxy.go:201-212
+        except _lib.TfscError as e:
+            context.abort(getattr(grpc.StatusCode, _GRPC_CODE.get(e.code, "INTERNAL")), str(e))
+
+    def unsupported(name):
+        def fn(request: bytes, context):
+            # MultiInference is rejected by the reference too (tfservingproxy.go:215-217); Classify/Regress need
+            # tf.Example signatures that the predict-only model templates of this build do not export
+            context.abort(grpc.StatusCode.UNIMPLEMENTED, f"{name} not supported")
+        return fn
+
+    health_status = {"serving": True}
+
+    def health_check(request: bytes, context):
+        return b"\x08\x01" if health_status["serving"] else b"\x08\x02"  # HealthCheckResponse{status}
+
+    methods = {"Predict": grpc.unary_unary_rpc_method_handler(predict, ident, ident)}
+    for m in ("Classify", "Regress", "MultiInference", "GetModelMetadata"):
+        methods[m] = grpc.unary_unary_rpc_method_handler(unsupported(m), ident, ident)
+    server = grpc.server(futures.ThreadPoolExecutor(max_workers=workers),
+                         options=[("grpc.max_receive_message_length", max_msg), ("grpc.max_send_message_length", max_msg)])
+    server.add_generic_rpc_handlers((
+        grpc.method_handlers_generic_handler("tensorflow.serving.PredictionService", methods),
+        grpc.method_handlers_generic_handler("tensorflow.serving.SessionService",
+                                             {"SessionRun": grpc.unary_unary_rpc_method_handler(unsupported("SessionRun"), ident, ident)}),
+        grpc.method_handlers_generic_handler("grpc.health.v1.Health",
+                                             {"Check": grpc.unary_unary_rpc_method_handler(health_check, ident, ident)}),
+    ))
+    bound = server.add_insecure_port(f"{host}:{port}")
+    server.set_health = lambda ok: health_status.__setitem__("serving", bool(ok))  # GrpcProxy.SetHealth, :151-157
+    server.bound_port = bound
+    return server
+
+
+def main(argv=None):
+    argv = sys.argv[1:] if argv is None else argv
+    cfg = load_config(argv[0] if argv else "config.yaml")
+    srv = Server(cfg)
+    rest = make_rest_server(srv, int(cfg.get("cacheRestPort", 8094)))
+    max_msg = int(cfg.get("serving.grpcMaxMsgSize") or 16 * 1024 * 1024)
+    grpc_srv = make_grpc_server(srv, int(cfg.get("cacheGrpcPort", 8095)), max_msg)
+    grpc_srv.start()
+    threading.Thread(target=rest.serve_forever, daemon=True).start()
+    print(f"tfservingcache_b200: REST :{rest.server_port}  gRPC :{grpc_srv.bound_port}  nodes={srv.num_nodes}", flush=True)
+    try:
+        grpc_srv.wait_for_termination()
+    except KeyboardInterrupt:
+        pass
+    finally:
+        rest.shutdown()
+        srv.close()
+
+
+if __name__ == "__main__":
+    main()
