@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=48, help="requests in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident part alone")
+    ap.add_argument("--light-clients", type=int, default=16, help="clients per GPU of the light-load latency probe (0 = skip)")
     ap.add_argument("--dims", type=int, nargs="*", default=None, help="override model dims (debug only)")
     ap.add_argument("--replica-pick", default="hot-spread", choices=["hot-spread", "random", "first"],
                     help="replica choice among the ring's GetN candidates (reference: random)")
@@ -291,13 +292,16 @@ def run_b200(args):
     outputs_h = torch.empty(args.clients, out_dim).pin_memory()
     predict_ptr = C.cast(_lib.lib.tfsc_predict, C.c_void_p)
 
-    def e2e_run(step_lo, step_hi, want_lat):
+    def e2e_run(step_lo, step_hi, want_lat, clients=None, limit=None):
+        clients = clients or args.clients
         req = np.concatenate([step_groups(wl, rank, s, tick_global)[0] for s in range(step_lo, step_hi)]).astype(np.int32)
+        if limit:
+            req = req[:limit]
         lat = np.zeros(len(req), np.float32)
         el = C.c_double()
         failed = lg.tfsc_loadgen_run(predict_ptr, C.c_void_p(srv._h), names, 16, b"1", req.ctypes.data_as(C.c_void_p),
                                      C.c_int64(len(req)), C.c_void_p(inputs_h.data_ptr()), C.c_int64(n_inputs), in_dim,
-                                     C.c_void_p(outputs_h.data_ptr()), out_dim, args.clients,
+                                     C.c_void_p(outputs_h.data_ptr()), out_dim, clients,
                                      lat.ctypes.data_as(C.c_void_p) if want_lat else None, C.byref(el))
         return len(req), failed, el.value, lat
 
@@ -312,6 +316,12 @@ def run_b200(args):
         n_e2e, failed, el_s, lat = e2e_run(e0 + W, e0 + W + e2e_steps, True)
     torch.cuda.synchronize()
     ste1 = srv.stats()
+    # light-load latency probe (north_star: cache-hit p50 < 5 ms): same trace, few closed-loop clients
+    light = None
+    if args.light_clients > 0 and not args.skip_e2e:
+        n_l, f_l, el_l, lat_l = e2e_run(e0 + W, e0 + W + e2e_steps, True, clients=args.light_clients, limit=args.light_clients * 64)
+        light = {"clients_per_gpu": args.light_clients, "requests": int(n_l), "qps_rank0": round(n_l / el_l, 1),
+                 "p50_ms": round(float(np.percentile(lat_l, 50)) / 1e3, 3), "p99_ms": round(float(np.percentile(lat_l, 99)) / 1e3, 3)}
     if world > 1:
         tt = torch.tensor([elapsed_ms, el_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -357,7 +367,8 @@ def run_b200(args):
                     "d2h_bytes_per_step": int((ste1["d2h_output_bytes"] - ste0["d2h_output_bytes"]) / e2e_steps),
                     "clients_per_gpu": args.clients, "steps": e2e_steps, "failed": failed_all,
                     "p50_ms": round(float(np.percentile(lat, 50)) / 1e3, 3), "p99_ms": round(float(np.percentile(lat, 99)) / 1e3, 3),
-                    "mean_batch_rows": round((ste1["batched_rows"] - ste0["batched_rows"]) / max(1, ste1["batches"] - ste0["batches"]), 2)},
+                    "mean_batch_rows": round((ste1["batched_rows"] - ste0["batched_rows"]) / max(1, ste1["batches"] - ste0["batches"]), 2),
+                    "light_load": light},
             "hbm_cache_hit_pct": round(100.0 * (st1["cache_hits_total"] - st0["cache_hits_total"]) / max(1, st1["cache_total"] - st0["cache_total"]), 2),
             "gpu_launches": int(launches_all),
             "clocks": clocks,

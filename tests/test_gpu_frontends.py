@@ -88,3 +88,15 @@ def test_grpc_proxy_predict_and_errors(endpoints):
     st = srv.stats()
     assert st["proxy_requests_grpc"] >= 2 and st["proxy_failures_grpc"] >= 1
     ch.close()
+
+
+def test_metrics_endpoint_keeps_reference_metric_names(endpoints):
+    _srv, base, _ = endpoints
+    st, body = _http(f"{base}/monitoring/prometheus/metrics")
+    text = body.decode()
+    assert st == 200
+    for name in ("tfservingcache_cache_total", "tfservingcache_cache_hits_total", "tfservingcache_cache_misses_total",
+                 "tfservingcache_cache_duration_seconds", "tfservingcache_cache_fetch_duration_seconds",
+                 "tfservingcache_proxy_requests_total", "tfservingcache_proxy_failures_total", "tfservingcache_hbm_cache_hit_ratio"):
+        assert f"# TYPE {name} " in text
+    assert 'tfservingcache_cache_total{model="all_models",version="-1"}' in text

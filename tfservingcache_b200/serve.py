@@ -23,13 +23,53 @@ _GRPC_CODE = {_lib.E_INVALID: "INVALID_ARGUMENT", _lib.E_TIMEOUT: "DEADLINE_EXCE
               _lib.E_NO_DEVICE: "UNAVAILABLE", _lib.E_EMPTY_RING: "UNAVAILABLE", _lib.E_BUFFER: "INTERNAL"}
 
 
-def make_rest_server(srv: Server, port: int, host: str = "0.0.0.0") -> ThreadingHTTPServer:
+def prometheus_text(srv: Server) -> bytes:
+    """Exposition of the reference's metric names (cachemanager.go:24-43, tfservingproxy.go:25-32; labels collapse
+    to all_models/-1 as with metrics.modelLabels=false) plus the HBM-side additions of this build."""
+    st = srv.stats()
+    lab = '{model="all_models",version="-1"}'
+    lines = []
+
+    def add(name, kind, help_, samples):
+        lines.append(f"# HELP {name} {help_}")
+        lines.append(f"# TYPE {name} {kind}")
+        lines.extend(samples)
+
+    add("tfservingcache_cache_total", "counter", "The total number of cache misses and hits", [f"tfservingcache_cache_total{lab} {st['cache_total']}"])
+    add("tfservingcache_cache_hits_total", "counter", "The total number of cache hits", [f"tfservingcache_cache_hits_total{lab} {st['cache_hits_total']}"])
+    add("tfservingcache_cache_misses_total", "counter", "The total number of cache misses", [f"tfservingcache_cache_misses_total{lab} {st['cache_misses_total']}"])
+    add("tfservingcache_cache_duration_seconds", "summary", "The duration of cache requests, including hits and misses",
+        [f"tfservingcache_cache_duration_seconds_sum{lab} {st['cache_duration_seconds_sum']}", f"tfservingcache_cache_duration_seconds_count{lab} {st['cache_total']}"])
+    add("tfservingcache_cache_fetch_duration_seconds", "summary", "The duration of cache fetches (when cache miss)",
+        [f"tfservingcache_cache_fetch_duration_seconds_sum{lab} {st['cache_fetch_duration_seconds_sum']}", f"tfservingcache_cache_fetch_duration_seconds_count{lab} {st['cache_misses_total']}"])
+    add("tfservingcache_proxy_requests_total", "counter", "The total number of requests",
+        [f'tfservingcache_proxy_requests_total{{protocol="rest"}} {st["proxy_requests_rest"]}', f'tfservingcache_proxy_requests_total{{protocol="grpc"}} {st["proxy_requests_grpc"]}'])
+    add("tfservingcache_proxy_failures_total", "counter", "The total number of failed requests",
+        [f'tfservingcache_proxy_failures_total{{protocol="rest"}} {st["proxy_failures_rest"]}', f'tfservingcache_proxy_failures_total{{protocol="grpc"}} {st["proxy_failures_grpc"]}'])
+    ratio = st["cache_hits_total"] / st["cache_total"] if st["cache_total"] else 0.0
+    add("tfservingcache_hbm_cache_hit_ratio", "gauge", "cache_hits_total / cache_total (BASELINE metric 'HBM cache hit %')", [f"tfservingcache_hbm_cache_hit_ratio {ratio}"])
+    for k in ("arena_bytes_used", "arena_bytes_capacity", "resident_models", "host_models"):
+        add(f"tfservingcache_{k}", "gauge", k.replace("_", " "), [f"tfservingcache_{k} {st[k]}"])
+    for k in ("h2d_weight_bytes", "h2d_input_bytes", "d2h_output_bytes", "evictions_hbm", "evictions_host", "batches", "batched_rows", "kernel_launches"):
+        add(f"tfservingcache_{k}_total", "counter", k.replace("_", " "), [f"tfservingcache_{k}_total {st[k]}"])
+    return ("\n".join(lines) + "\n").encode()
+
+
+def make_rest_server(srv: Server, port: int, host: str = "0.0.0.0", metrics_path: str = "/monitoring/prometheus/metrics") -> ThreadingHTTPServer:
     class Handler(BaseHTTPRequestHandler):
         protocol_version = "HTTP/1.1"
 
         def _serve(self):
             n = int(self.headers.get("Content-Length") or 0)
             body = self.rfile.read(n) if n else b""
+            if self.command == "GET" and self.path.split("?")[0] == metrics_path:  # metrics.path (MetricsHandler, metrics.go:16)
+                out = prometheus_text(srv)
+                self.send_response(200)
+                self.send_header("Content-Type", "text/plain; version=0.0.4")
+                self.send_header("Content-Length", str(len(out)))
+                self.end_headers()
+                self.wfile.write(out)
+                return
             status, out = srv.rest_handle(self.command, self.path, body)   # RestProxy.Serve, tfservingproxy.go:93-129
             self.send_response(status)
             self.send_header("Content-Type", "application/json")
@@ -92,7 +132,7 @@ def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
     cfg = load_config(argv[0] if argv else "config.yaml")
     srv = Server(cfg)
-    rest = make_rest_server(srv, int(cfg.get("cacheRestPort", 8094)))
+    rest = make_rest_server(srv, int(cfg.get("cacheRestPort", 8094)), metrics_path=str(cfg.get("metrics.path", "/monitoring/prometheus/metrics")))
     max_msg = int(cfg.get("serving.grpcMaxMsgSize") or 16 * 1024 * 1024)
     grpc_srv = make_grpc_server(srv, int(cfg.get("cacheGrpcPort", 8095)), max_msg)
     grpc_srv.start()
