@@ -129,4 +129,102 @@ def forward(man: dict, blob: np.ndarray, x: np.ndarray, dtype=np.float32) -> np.
             if L["activation"] == "relu":
                 h = np.maximum(h, dtype(0))
         return h
+    if t == "graph":
+        return graph_forward(man, blob, x, dtype)
     raise ValueError(f"unknown template {t}")
+
+
+def resnet50_ops(image=224, classes=1000):
+    """Independent restatement of the ResNet-50 v1.5 topology (He et al. 2015; stride on the 3x3 conv as in
+    torchvision / the TF official model), expressed in the bundle's op list."""
+    ops = []
+    cfg = [(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)]
+    size = image
+    ops.append(dict(op="conv", src=-1, dst=0, h=size, w=size, c=3, kh=7, kw=7, stride=2, pad=3, cout=64, act="relu"))
+    size = (size + 2 * 3 - 7) // 2 + 1
+    ops.append(dict(op="maxpool", src=0, dst=1, h=size, w=size, c=64, kh=3, kw=3, stride=2, pad=1))
+    size = (size + 2 - 3) // 2 + 1
+    cur, cin = 1, 64
+    for planes, n_blocks, first_stride in cfg:
+        for blk in range(n_blocks):
+            stride = first_stride if blk == 0 else 1
+            others = [i for i in range(5) if i != cur]
+            t1, t2, t3, t4 = others[0], others[1], others[2], others[3]
+            out_size = (size + 2 - 3) // stride + 1
+            ops.append(dict(op="conv", src=cur, dst=t1, h=size, w=size, c=cin, kh=1, kw=1, stride=1, pad=0, cout=planes, act="relu"))
+            ops.append(dict(op="conv", src=t1, dst=t2, h=size, w=size, c=planes, kh=3, kw=3, stride=stride, pad=1, cout=planes, act="relu"))
+            shortcut = cur
+            if blk == 0:
+                ops.append(dict(op="conv", src=cur, dst=t3, h=size, w=size, c=cin, kh=1, kw=1, stride=stride, pad=0, cout=4 * planes, act="none"))
+                shortcut = t3
+            ops.append(dict(op="conv", src=t2, dst=t4, res=shortcut, h=out_size, w=out_size, c=planes, kh=1, kw=1, stride=1, pad=0,
+                            cout=4 * planes, act="relu"))
+            cur, cin, size = t4, 4 * planes, out_size
+    t1 = [i for i in range(5) if i != cur][0]
+    ops.append(dict(op="avgpool", src=cur, dst=t1, h=size, w=size, c=cin))
+    ops.append(dict(op="dense", src=t1, dst=-2, h=1, w=1, c=cin, cout=classes, act="none"))
+    return ops
+
+
+def graph_manifest(input_shape, ops, n_buffers=5):
+    off = 0
+    for o in ops:
+        if o["op"] in ("conv", "dense"):
+            k = o.get("kh", 1) * o.get("kw", 1) * o["c"]
+            o["w_offset"] = off
+            off = align256(off + k * o["cout"] * 4)
+            o["b_offset"] = off
+            off = align256(off + o["cout"] * 4)
+    return {"format": "tfsc-b200-v1", "template": "graph", "dtype": "float32", "signature": {"input": "x", "output": "y"},
+            "input_shape": list(input_shape), "n_buffers": n_buffers, "ops": ops, "weights_bytes": off}
+
+
+def synth_graph_blob(man: dict, seed: int) -> np.ndarray:
+    blob = np.zeros(man["weights_bytes"] // 4, dtype=np.float32)
+    for i, o in enumerate(man["ops"]):
+        if o["op"] not in ("conv", "dense"):
+            continue
+        fan_in = o.get("kh", 1) * o.get("kw", 1) * o["c"]
+        w = synth_tensor(seed, 2 * i, fan_in * o["cout"], weight_scale(fan_in))
+        b = synth_tensor(seed, 2 * i + 1, o["cout"], BIAS_SCALE)
+        blob[o["w_offset"] // 4: o["w_offset"] // 4 + w.size] = w
+        blob[o["b_offset"] // 4: o["b_offset"] // 4 + b.size] = b
+    return blob
+
+
+def graph_forward(man: dict, blob: np.ndarray, x: np.ndarray, dtype=np.float64) -> np.ndarray:
+    """Interpreter of a graph bundle with torch-CPU functional ops (conv2d / max_pool2d) in `dtype`; NHWC in and
+    out, NCHW inside."""
+    import torch
+    import torch.nn.functional as F
+    td = torch.float64 if dtype == np.float64 else torch.float32
+    ish = man["input_shape"]
+    xb = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).reshape(-1, *ish).to(td)
+    bufs = {-1: xb.permute(0, 3, 1, 2).contiguous()}
+    for o in man["ops"]:
+        src = bufs[o["src"]]
+        if o["op"] in ("conv", "dense"):
+            kh, kw, c, cout = o.get("kh", 1), o.get("kw", 1), o["c"], o["cout"]
+            w = torch.from_numpy(blob[o["w_offset"] // 4: o["w_offset"] // 4 + kh * kw * c * cout].reshape(kh, kw, c, cout)).to(td)
+            b = torch.from_numpy(blob[o["b_offset"] // 4: o["b_offset"] // 4 + cout]).to(td)
+            if o["op"] == "dense":
+                y = src.reshape(src.shape[0], -1) @ w.reshape(c, cout) + b
+                y = y.reshape(src.shape[0], cout, 1, 1)
+            else:
+                y = F.conv2d(src, w.permute(3, 2, 0, 1).contiguous(), b, stride=o["stride"], padding=o["pad"])
+            if o.get("res", -100) != -100:
+                y = y + bufs[o["res"]]
+            if o.get("act", "none") == "relu":
+                y = torch.relu(y)
+            elif o.get("act") == "gelu":
+                y = F.gelu(y)
+        elif o["op"] == "maxpool":
+            y = F.max_pool2d(src, (o["kh"], o["kw"]), stride=o["stride"], padding=o["pad"])
+        elif o["op"] == "avgpool":
+            y = src.mean(dim=(2, 3), keepdim=True)
+        else:
+            raise ValueError(o["op"])
+        bufs[o["dst"]] = y
+    out = bufs[-2]
+    out = out.permute(0, 2, 3, 1).reshape(out.shape[0], -1) if out.shape[2] * out.shape[3] == 1 else out.permute(0, 2, 3, 1)
+    return out.numpy().astype(dtype)

@@ -1,0 +1,118 @@
+"""-m gpu: X4 -- conv-net building blocks and the graph executor (ResNet-50 bundle) vs the oracle
+(torch-CPU fp64 functional conv2d / max_pool2d on the same blob).  Tolerance 1e-4 relative to max(1,|ref|)."""
+import numpy as np
+import pytest
+
+import tfservingcache_b200 as t
+from oracle import models
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+lib = t._lib.lib
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _err(got, ref):
+    return float(np.max(np.abs(np.asarray(got, np.float64) - ref) / np.maximum(1.0, np.abs(ref))))
+
+
+@pytest.mark.parametrize("m,n,k,lda", [(1, 8, 4, 4), (49, 64, 147, 148), (200, 100, 37, 37), (128, 64, 16, 16), (300, 1000, 2048, 2048),
+                                        (3136, 256, 64, 64), (130, 66, 18, 20)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_k_gemm(m, n, k, lda, act):
+    torch = _torch()
+    rng = np.random.default_rng(m * 7 + n + k + act)
+    a = rng.standard_normal((m, lda)).astype(np.float32)
+    b = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32)
+    r = rng.standard_normal((m, n)).astype(np.float32)
+    ad, bd, biasd, rd = (torch.from_numpy(v).cuda() for v in (a, b, bias, r))
+    cd = torch.full((m, n), float("nan"), device="cuda")
+    t._lib.check(lib.tfsc_k_gemm(ad.data_ptr(), bd.data_ptr(), biasd.data_ptr(), rd.data_ptr(), cd.data_ptr(), m, n, k, lda, act, None))
+    torch.cuda.synchronize()
+    ref = a[:, :k].astype(np.float64) @ b.astype(np.float64) + bias + r
+    if act == 1:
+        ref = np.maximum(ref, 0)
+    elif act == 2:
+        ref = torch.nn.functional.gelu(torch.from_numpy(ref)).numpy()
+    assert _err(cd.cpu().numpy(), ref) <= TOL
+
+
+@pytest.mark.parametrize("h,c,kh,stride,pad,cout", [(16, 3, 7, 2, 3, 8), (14, 16, 3, 1, 1, 24), (14, 16, 3, 2, 1, 24), (9, 5, 1, 2, 0, 7)])
+def test_conv_as_im2col_gemm_matches_torch(h, c, kh, stride, pad, cout):
+    torch = _torch()
+    rng = np.random.default_rng(h + c + kh)
+    bsz = 3
+    x = rng.standard_normal((bsz, h, h, c)).astype(np.float32)
+    w = (rng.standard_normal((kh, kh, c, cout)) / np.sqrt(kh * kh * c)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    oh = (h + 2 * pad - kh) // stride + 1
+    kk = kh * kh * c
+    ldc = (kk + 3) // 4 * 4
+    xd, wd, bd = (torch.from_numpy(v).cuda() for v in (x, w, b))
+    col = torch.full((bsz * oh * oh, ldc), float("nan"), device="cuda")
+    y = torch.empty(bsz * oh * oh, cout, device="cuda")
+    t._lib.check(lib.tfsc_k_im2col(xd.data_ptr(), col.data_ptr(), bsz, h, h, c, kh, kh, stride, pad, ldc, None))
+    t._lib.check(lib.tfsc_k_gemm(col.data_ptr(), wd.data_ptr(), bd.data_ptr(), None, y.data_ptr(), bsz * oh * oh, cout, kk, ldc, 1, None))
+    torch.cuda.synchronize()
+    ref = torch.relu(torch.nn.functional.conv2d(torch.from_numpy(x).double().permute(0, 3, 1, 2),
+                                                torch.from_numpy(w).double().permute(3, 2, 0, 1),
+                                                torch.from_numpy(b).double(), stride=stride, padding=pad)).permute(0, 2, 3, 1).numpy()
+    assert _err(y.cpu().numpy().reshape(bsz, oh, oh, cout), ref) <= TOL
+
+
+def test_pools_match_torch():
+    torch = _torch()
+    x = torch.randn(2, 13, 13, 10)
+    xd = x.cuda()
+    y = torch.empty(2, 7, 7, 10, device="cuda")
+    t._lib.check(lib.tfsc_k_maxpool(xd.data_ptr(), y.data_ptr(), 2, 13, 13, 10, 3, 3, 2, 1, None))
+    ref = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(y.cpu(), ref)
+    a = torch.empty(2, 10, device="cuda")
+    t._lib.check(lib.tfsc_k_avgpool(xd.data_ptr(), a.data_ptr(), 2, 169, 10, None))
+    assert torch.allclose(a.cpu(), x.mean(dim=(1, 2)), atol=1e-6)
+
+
+def _server(man, count=8, arena=1 << 30, **kw):
+    cfg = {"modelProvider.type": "synthetic", "modelProvider.synthetic.template": "manifest",
+           "modelProvider.synthetic.manifest": man, "modelProvider.synthetic.count": count, "gpu.devices": [0],
+           "gpu.arenaBytes": arena, "serving.maxConcurrentModels": 4, "modelCache.size": 4 << 30, "gpu.maxBatch": 8}
+    cfg.update(kw)
+    return t.Server(cfg)
+
+
+def test_small_resnet_through_server_matches_oracle():
+    _torch()
+    man = t.modelformat.resnet50_manifest(image=64, classes=10)
+    oman = models.graph_manifest([64, 64, 3], models.resnet50_ops(64, 10))
+    rng = np.random.default_rng(0)
+    with _server(man, arena=256 << 20) as srv:
+        for j, bsz in [(0, 1), (3, 5), (0, 2)]:
+            x = rng.random((bsz, 64, 64, 3)).astype(np.float32)
+            y = srv.predict(f"m{j}", "1", x)
+            ref = models.graph_forward(oman, models.synth_graph_blob(oman, 1000 + j), x, np.float64)
+            assert y.shape == (bsz, 10) and _err(y, ref) <= TOL
+        st = srv.stats()
+        assert st["cache_misses_total"] == 2 and st["cache_hits_total"] == 1
+
+
+def test_resnet50_full_size_matches_oracle_and_rest():
+    """BASELINE configs[1] model: ResNet-50, 224x224x3, 25.5 M parameters (102 MB)."""
+    _torch()
+    import json
+    man = t.modelformat.resnet50_manifest()
+    assert man["weights_bytes"] == models.graph_manifest([224, 224, 3], models.resnet50_ops())["weights_bytes"] == 102121984
+    oman = models.graph_manifest([224, 224, 3], models.resnet50_ops())
+    x = np.random.default_rng(1).random((2, 224, 224, 3)).astype(np.float32)
+    with _server(man) as srv:
+        y = srv.predict("m1", "1", x)
+        st = srv.stats()
+    ref = models.graph_forward(oman, models.synth_graph_blob(oman, 1001), x, np.float64)
+    assert y.shape == (2, 1000) and _err(y, ref) <= TOL
+    assert st["h2d_weight_bytes"] == 102121984

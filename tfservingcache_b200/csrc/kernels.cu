@@ -13,7 +13,8 @@ namespace tfsc {
 
 static std::atomic<int64_t> g_launches{0};
 extern std::atomic<int64_t> g_launches_tc;
-int64_t kernel_launch_count() { return g_launches.load() + g_launches_tc.load(); }
+extern std::atomic<int64_t> g_launches_nn;
+int64_t kernel_launch_count() { return g_launches.load() + g_launches_tc.load() + g_launches_nn.load(); }
 
 // ------------------------------------------------------------------------------------ X1 ----
 __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n,

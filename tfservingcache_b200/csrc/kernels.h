@@ -25,6 +25,15 @@ size_t dense_tc_workspace_bytes(int k, int n);
 cudaError_t launch_dense_tc(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n,
                             bool relu, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
+// X4/X5 building blocks (nn_kernels.cu): act 0 none / 1 relu / 2 gelu(erf)
+cudaError_t launch_gemm(const float* A, const float* B, const float* bias, const float* R, float* C, int M, int N, int K,
+                        int lda, int act, cudaStream_t s);
+cudaError_t launch_im2col(const float* x, float* col, int Bn, int H, int W, int C, int KH, int KW, int stride, int pad,
+                          int OH, int OW, int ldc, cudaStream_t s);
+cudaError_t launch_maxpool(const float* x, float* y, int Bn, int H, int W, int C, int KH, int KW, int stride, int pad, int OH,
+                           int OW, cudaStream_t s);
+cudaError_t launch_avgpool(const float* x, float* y, int Bn, int HW, int C, cudaStream_t s);
+
 int64_t kernel_launch_count();
 
 }  // namespace tfsc

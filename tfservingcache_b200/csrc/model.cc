@@ -1,10 +1,25 @@
 #include "model.h"
 
+#include <algorithm>
+
 namespace tfsc {
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+size_t ModelDesc::scratch_bytes(int64_t rows) const {
+  if (tmpl == Template::Mlp) return 2 * (((size_t)rows * (size_t)(max_width > 0 ? max_width : 1) * 4 + 255) & ~(size_t)255);
+  if (tmpl == Template::Graph) return ((size_t)rows * (size_t)(n_buffers * buf_elems + col_elems) * 4 + 255) & ~(size_t)255;
+  return 256;
+}
+
 static void finish(ModelDesc* d) {
+  if (d->tmpl == Template::Graph) {
+    d->in_dim = 1;
+    for (auto v : d->input_shape) d->in_dim *= v;
+    d->out_dim = 1;
+    for (auto v : d->output_shape) d->out_dim *= v;
+    return;
+  }
   if (d->tmpl == Template::Mlp) {
     d->in_dim = d->layers.front().in;
     d->out_dim = d->layers.back().out;
@@ -103,6 +118,107 @@ bool parse_manifest(const Json& j, ModelDesc* d, std::string* err) {
       prev_out = L.out;
       d->layers.push_back(L);
     }
+  } else if (t == "graph") {
+    d->tmpl = Template::Graph;
+    const Json* ops = j.get("ops");
+    const Json* ish = j.get("input_shape");
+    if (!ops || ops->type != Json::Arr || ops->arr.empty() || !ish || ish->type != Json::Arr) {
+      *err = "graph manifest needs 'ops' and 'input_shape'";
+      return false;
+    }
+    for (auto& v : ish->arr) d->input_shape.push_back(v.integer());
+    d->n_buffers = (int)j.get_int("n_buffers", 0);
+    if (d->n_buffers < 1 || d->n_buffers > 16) {
+      *err = "graph manifest: n_buffers out of range";
+      return false;
+    }
+    int64_t in_elems = 1;
+    for (auto v : d->input_shape) in_elems *= v;
+    std::vector<int64_t> written(d->n_buffers, -1);  // elements per image held by each scratch buffer
+    int64_t out_elems = -1;
+    for (auto& oj : ops->arr) {
+      GraphOp o;
+      const std::string kind = oj.get_str("op", "");
+      if (kind == "conv") o.kind = OpKind::Conv;
+      else if (kind == "maxpool") o.kind = OpKind::MaxPool;
+      else if (kind == "avgpool") o.kind = OpKind::AvgPool;
+      else if (kind == "dense") o.kind = OpKind::Dense;
+      else {
+        *err = "graph manifest: unknown op '" + kind + "'";
+        return false;
+      }
+      o.src = (int)oj.get_int("src", -1);
+      o.dst = (int)oj.get_int("dst", 0);
+      o.res = (int)oj.get_int("res", -100);
+      o.h = (int)oj.get_int("h", 1);
+      o.w = (int)oj.get_int("w", 1);
+      o.c = (int)oj.get_int("c", 1);
+      o.kh = (int)oj.get_int("kh", 1);
+      o.kw = (int)oj.get_int("kw", 1);
+      o.stride = (int)oj.get_int("stride", 1);
+      o.pad = (int)oj.get_int("pad", 0);
+      o.cout = (int)oj.get_int("cout", o.c);
+      const std::string act = oj.get_str("act", "none");
+      o.act = act == "relu" ? 1 : act == "gelu" ? 2 : 0;
+      o.w_off = (size_t)oj.get_int("w_offset", 0);
+      o.b_off = (size_t)oj.get_int("b_offset", 0);
+      if (o.h < 1 || o.w < 1 || o.c < 1 || o.kh < 1 || o.kw < 1 || o.stride < 1 || o.pad < 0 || o.cout < 1) {
+        *err = "graph manifest: bad op geometry";
+        return false;
+      }
+      if (o.kind == OpKind::AvgPool) {
+        o.oh = o.ow = 1;
+        o.cout = o.c;
+      } else if (o.kind == OpKind::Dense) {
+        o.oh = o.ow = 1;
+        o.kh = o.kw = 1;
+      } else {
+        o.oh = (o.h + 2 * o.pad - o.kh) / o.stride + 1;
+        o.ow = (o.w + 2 * o.pad - o.kw) / o.stride + 1;
+        if (o.kind == OpKind::MaxPool) o.cout = o.c;
+      }
+      const int64_t in_e = (int64_t)o.h * o.w * o.c, out_e = (int64_t)o.oh * o.ow * o.cout;
+      auto buf_ok = [&](int b) { return b == -1 || (b >= 0 && b < d->n_buffers); };
+      if (!buf_ok(o.src) || !(o.dst == -2 || (o.dst >= 0 && o.dst < d->n_buffers)) || (o.res != -100 && !buf_ok(o.res)) ||
+          o.dst == o.src || o.dst == o.res) {
+        *err = "graph manifest: bad buffer index";
+        return false;
+      }
+      const int64_t have = o.src == -1 ? in_elems : written[o.src];
+      if (have != in_e || (o.res != -100 && (o.res == -1 ? in_elems : written[o.res]) != out_e)) {
+        *err = "graph manifest: op input size does not match its producer";
+        return false;
+      }
+      if (o.kind == OpKind::Conv || o.kind == OpKind::Dense) {
+        const size_t wbytes = (size_t)o.kh * o.kw * o.c * o.cout * 4;
+        if ((o.w_off & 255) || (o.b_off & 255) || o.w_off + wbytes > d->weights_bytes || o.b_off + (size_t)o.cout * 4 > d->weights_bytes) {
+          *err = "graph manifest: weights out of range or misaligned";
+          return false;
+        }
+        const bool direct = o.kh == 1 && o.kw == 1 && o.stride == 1 && o.pad == 0;
+        if (!direct) {
+          const int64_t ldc = ((int64_t)o.kh * o.kw * o.c + 3) / 4 * 4;
+          d->col_elems = std::max<int64_t>(d->col_elems, (int64_t)o.oh * o.ow * ldc);
+        }
+      }
+      if (o.dst == -2) out_elems = out_e;
+      else {
+        written[o.dst] = out_e;
+        d->buf_elems = std::max<int64_t>(d->buf_elems, out_e);
+      }
+      d->ops.push_back(o);
+    }
+    if (out_elems < 0 || d->ops.back().dst != -2) {
+      *err = "graph manifest: the last op must write the response (dst = -2)";
+      return false;
+    }
+    d->output_shape.clear();
+    const GraphOp& last = d->ops.back();
+    if (last.oh * last.ow > 1) {
+      d->output_shape.push_back(last.oh);
+      d->output_shape.push_back(last.ow);
+    }
+    d->output_shape.push_back(last.cout);
   } else {
     *err = "unknown template '" + t + "'";
     return false;

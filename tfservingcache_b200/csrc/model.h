@@ -12,7 +12,20 @@
 
 namespace tfsc {
 
-enum class Template { Affine, Mlp };
+enum class Template { Affine, Mlp, Graph };
+
+// One node of a "graph" bundle (conv nets): activations are NHWC fp32, `src`/`dst`/`res` index scratch
+// activation buffers (-1 = the request tensor, -2 = the response tensor). Weights: conv/dense kernel
+// flattened to [kh*kw*c, cout] row-major (= TF HWIO / dense layout) at w_off, bias (folded BN) at b_off.
+enum class OpKind { Conv, MaxPool, AvgPool, Dense };
+struct GraphOp {
+  OpKind kind = OpKind::Conv;
+  int src = -1, dst = 0, res = -100;  // res = -100: no residual input
+  int h = 1, w = 1, c = 1;            // input H, W, C per image
+  int kh = 1, kw = 1, stride = 1, pad = 0, cout = 1, oh = 1, ow = 1;
+  int act = 0;                        // 0 none, 1 relu, 2 gelu
+  size_t w_off = 0, b_off = 0;
+};
 
 struct DenseLayer {
   int in = 0, out = 0;
@@ -29,6 +42,15 @@ struct ModelDesc {
   // elements per batch row; 0 = elementwise / any shape (Affine)
   int64_t in_dim = 0, out_dim = 0;
   int max_width = 0;  // widest activation (for scratch sizing)
+  // Graph
+  std::vector<GraphOp> ops;
+  int n_buffers = 0;
+  int64_t buf_elems = 0;  // largest activation, elements per image
+  int64_t col_elems = 0;  // largest im2col matrix, elements per image
+  std::vector<int64_t> input_shape;   // per image, e.g. [224,224,3]
+  std::vector<int64_t> output_shape;  // per image, e.g. [1000]
+  // bytes of executor scratch (activation buffers + im2col) for `rows` images / batch rows
+  size_t scratch_bytes(int64_t rows) const;
 };
 
 bool parse_manifest(const Json& j, ModelDesc* d, std::string* err);

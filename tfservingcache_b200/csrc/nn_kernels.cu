@@ -1,0 +1,226 @@
+// Dense-net building blocks for the graph executor, fp32, sm_100a:
+//   gemm_f32      C[M,N] = act(A[M,K] B[K,N] + bias[N] (+ R[M,N]))   register-tiled FFMA GEMM (exact fp32)
+//   im2col_nhwc   NHWC activations -> [B*OH*OW, KH*KW*C (padded to x4)] patch matrix (conv = im2col + GEMM with
+//                 the TF HWIO kernel flattened to [KH*KW*Cin, Cout]; 1x1/stride-1 convs skip it)
+//   maxpool / global average pool (NHWC), embedding gather + LayerNorm, residual LayerNorm, attention
+// These are the round-1 functional kernels (CUDA-core FFMA keeps the 1e-4 fp32 contract trivially); the
+// tcgen05 3xTF32 machinery of dense_tc.cu is the planned replacement for the GEMM.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cfloat>
+
+#include "kernels.h"
+
+namespace tfsc {
+
+extern std::atomic<int64_t> g_launches_nn;
+std::atomic<int64_t> g_launches_nn{0};
+
+// ------------------------------------------------------------------------------------ GEMM ----
+constexpr int GBM = 128, GBN = 64, GBK = 16, GTHREADS = 256;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+template <bool VEC>
+__global__ void __launch_bounds__(GTHREADS)
+gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ bias,
+                const float* __restrict__ R, float* __restrict__ C, int M, int N, int K, int lda, int act) {
+  __shared__ __align__(16) float As[2][GBK][GBM + 4];
+  __shared__ __align__(16) float Bs[2][GBK][GBN];
+  const int tid = threadIdx.x;
+  const int ty = tid / 16, tx = tid % 16;  // 16 x 16 threads, 8 x 4 outputs each
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // global -> register staging: A tile 128 x 16 = 512 float4 (2 per thread), B tile 16 x 64 = 256 float4 (1 per thread)
+  float4 ra[2], rb;
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = tid / 4 + 64 * i, kq = (tid % 4) * 4;
+      const int gm = m0 + row, gk = k0 + kq;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gm < M) {
+        const float* p = A + (size_t)gm * lda + gk;
+        if (VEC && gk + 3 < K) v = __ldg(reinterpret_cast<const float4*>(p));
+        else {
+          if (gk < K) v.x = __ldg(p);
+          if (gk + 1 < K) v.y = __ldg(p + 1);
+          if (gk + 2 < K) v.z = __ldg(p + 2);
+          if (gk + 3 < K) v.w = __ldg(p + 3);
+        }
+      }
+      ra[i] = v;
+    }
+    {
+      const int kr = tid / 16, c4 = (tid % 16) * 4;
+      const int gk = k0 + kr, gn = n0 + c4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gk < K) {
+        const float* p = B + (size_t)gk * N + gn;
+        if (VEC && gn + 3 < N) v = __ldg(reinterpret_cast<const float4*>(p));
+        else {
+          if (gn < N) v.x = __ldg(p);
+          if (gn + 1 < N) v.y = __ldg(p + 1);
+          if (gn + 2 < N) v.z = __ldg(p + 2);
+          if (gn + 3 < N) v.w = __ldg(p + 3);
+        }
+      }
+      rb = v;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = tid / 4 + 64 * i, kq = (tid % 4) * 4;
+      As[buf][kq + 0][row] = ra[i].x;
+      As[buf][kq + 1][row] = ra[i].y;
+      As[buf][kq + 2][row] = ra[i].z;
+      As[buf][kq + 3][row] = ra[i].w;
+    }
+    const int kr = tid / 16, c4 = (tid % 16) * 4;
+    *reinterpret_cast<float4*>(&Bs[buf][kr][c4]) = rb;
+  };
+
+  const int nk = (K + GBK - 1) / GBK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * GBK);
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue: + bias (folded BN / dense bias), + residual, activation
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + ty * 8 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j] + (bias ? __ldg(bias + gn) : 0.f);
+      if (R) v += __ldg(R + (size_t)gm * N + gn);
+      if (act == 1) v = fmaxf(v, 0.f);
+      else if (act == 2) v = gelu_erf(v);
+      C[(size_t)gm * N + gn] = v;
+    }
+  }
+}
+
+cudaError_t launch_gemm(const float* A, const float* B, const float* bias, const float* R, float* C, int M, int N, int K,
+                        int lda, int act, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM);
+  const bool vec = (lda % 4 == 0) && (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  if (vec) gemm_f32_kernel<true><<<grid, GTHREADS, 0, s>>>(A, B, bias, R, C, M, N, K, lda, act);
+  else gemm_f32_kernel<false><<<grid, GTHREADS, 0, s>>>(A, B, bias, R, C, M, N, K, lda, act);
+  g_launches_nn++;
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------- im2col ----
+// col[(b*OH+oh)*OW+ow][(kh*KW+kw)*C + c] = x[b][oh*s-p+kh][ow*s-p+kw][c] (0 outside); row stride ldc >= KH*KW*C
+__global__ void __launch_bounds__(256)
+im2col_nhwc_kernel(const float* __restrict__ x, float* __restrict__ col, int Bn, int H, int W, int C, int KH, int KW,
+                   int stride, int pad, int OH, int OW, int ldc) {
+  const int64_t total = (int64_t)Bn * OH * OW * ldc;
+  const int Kreal = KH * KW * C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % ldc);
+    const int64_t row = idx / ldc;
+    float v = 0.f;
+    if (kk < Kreal) {
+      const int c = kk % C, kw = (kk / C) % KW, kh = kk / (C * KW);
+      const int ow = (int)(row % OW), oh = (int)((row / OW) % OH), b = (int)(row / ((int64_t)OW * OH));
+      const int ih = oh * stride - pad + kh, iw = ow * stride - pad + kw;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((int64_t)b * H + ih) * W + iw) * C + c);
+    }
+    col[idx] = v;
+  }
+}
+
+cudaError_t launch_im2col(const float* x, float* col, int Bn, int H, int W, int C, int KH, int KW, int stride, int pad,
+                          int OH, int OW, int ldc, cudaStream_t s) {
+  const int64_t total = (int64_t)Bn * OH * OW * ldc;
+  if (total <= 0) return cudaSuccess;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  im2col_nhwc_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, col, Bn, H, W, C, KH, KW, stride, pad, OH, OW, ldc);
+  g_launches_nn++;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ pools ----
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Bn, int H, int W, int C, int KH, int KW, int stride,
+                    int pad, int OH, int OW) {
+  const int64_t total = (int64_t)Bn * OH * OW * C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int ow = (int)((idx / C) % OW), oh = (int)((idx / ((int64_t)C * OW)) % OH), b = (int)(idx / ((int64_t)C * OW * OH));
+    float m = -FLT_MAX;
+    for (int kh = 0; kh < KH; ++kh)
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ih = oh * stride - pad + kh, iw = ow * stride - pad + kw;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) m = fmaxf(m, __ldg(x + (((int64_t)b * H + ih) * W + iw) * C + c));
+      }
+    y[idx] = m;
+  }
+}
+
+cudaError_t launch_maxpool(const float* x, float* y, int Bn, int H, int W, int C, int KH, int KW, int stride, int pad, int OH,
+                           int OW, cudaStream_t s) {
+  const int64_t total = (int64_t)Bn * OH * OW * C;
+  if (total <= 0) return cudaSuccess;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  maxpool_nhwc_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, y, Bn, H, W, C, KH, KW, stride, pad, OH, OW);
+  g_launches_nn++;
+  return cudaGetLastError();
+}
+
+// y[b][c] = mean over H*W of x[b][h][w][c]; sequential fp32 sum per (b,c): deterministic
+__global__ void __launch_bounds__(256)
+avgpool_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Bn, int HW, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Bn * C) return;
+  const int c = idx % C, b = idx / C;
+  const float* p = x + (size_t)b * HW * C + c;
+  float s = 0.f;
+  for (int i = 0; i < HW; ++i) s += __ldg(p + (size_t)i * C);
+  y[idx] = s / (float)HW;
+}
+
+cudaError_t launch_avgpool(const float* x, float* y, int Bn, int HW, int C, cudaStream_t s) {
+  if (Bn * C <= 0) return cudaSuccess;
+  avgpool_nhwc_kernel<<<(Bn * C + 255) / 256, 256, 0, s>>>(x, y, Bn, HW, C);
+  g_launches_nn++;
+  return cudaGetLastError();
+}
+
+}  // namespace tfsc

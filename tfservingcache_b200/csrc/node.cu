@@ -65,8 +65,7 @@ Node::~Node() {
     if (s.h_out) cudaFreeHost(s.h_out);
     if (s.d_in) cudaFree(s.d_in);
     if (s.d_out) cudaFree(s.d_out);
-    if (s.act0) cudaFree(s.act0);
-    if (s.act1) cudaFree(s.act1);
+    if (s.scratch) cudaFree(s.scratch);
     if (s.ws) cudaFree(s.ws);
     if (s.done) cudaEventDestroy(s.done);
     if (s.in_done) cudaEventDestroy(s.in_done);
@@ -451,13 +450,50 @@ size_t Node::model_ws_bytes(const ModelDesc& d) {
   return m;
 }
 
-cudaError_t Node::run_model(const DeviceModel& dm, const char* x, int64_t rows, char* y, char* act0, char* act1,
-                            void* ws, size_t ws_cap, cudaStream_t st) {
+cudaError_t Node::run_model(const DeviceModel& dm, const char* x, int64_t rows, char* y, char* scratch, void* ws,
+                            size_t ws_cap, cudaStream_t st) {
   const ModelDesc& d = dm.desc;
   if (d.tmpl == Template::Affine) {
     return launch_affine((const float*)x, (float*)y, rows, (const float*)(dm.dptr + d.a_off),
                          (const float*)(dm.dptr + d.b_off), st);
   }
+  if (d.tmpl == Template::Graph) {
+    // conv net: NHWC activations in `n_buffers` scratch buffers, conv = (im2col +) GEMM with fused bias /
+    // residual / ReLU epilogue (BN is folded into the kernel + bias when the bundle is written)
+    const size_t buf_bytes = (size_t)rows * d.buf_elems * 4;
+    char* col = scratch + (size_t)d.n_buffers * buf_bytes;
+    auto buf = [&](int i) -> char* { return i == -1 ? const_cast<char*>(x) : i == -2 ? y : scratch + (size_t)i * buf_bytes; };
+    const int B = (int)rows;
+    for (const GraphOp& o : d.ops) {
+      const float* src = (const float*)buf(o.src);
+      float* dst = (float*)buf(o.dst);
+      cudaError_t e = cudaSuccess;
+      if (o.kind == OpKind::Conv || o.kind == OpKind::Dense) {
+        const float* W = (const float*)(dm.dptr + o.w_off);
+        const float* bias = (const float*)(dm.dptr + o.b_off);
+        const float* res = o.res == -100 ? nullptr : (const float*)buf(o.res);
+        const int K = o.kh * o.kw * o.c;
+        const bool direct = o.kh == 1 && o.kw == 1 && o.stride == 1 && o.pad == 0;
+        const float* A = src;
+        int lda = K;
+        if (!direct) {
+          lda = (K + 3) / 4 * 4;
+          e = launch_im2col(src, (float*)col, B, o.h, o.w, o.c, o.kh, o.kw, o.stride, o.pad, o.oh, o.ow, lda, st);
+          if (e != cudaSuccess) return e;
+          A = (const float*)col;
+        }
+        e = launch_gemm(A, W, bias, res, dst, B * o.oh * o.ow, o.cout, K, lda, o.act, st);
+      } else if (o.kind == OpKind::MaxPool) {
+        e = launch_maxpool(src, dst, B, o.h, o.w, o.c, o.kh, o.kw, o.stride, o.pad, o.oh, o.ow, st);
+      } else {
+        e = launch_avgpool(src, dst, B, o.h * o.w, o.c, st);
+      }
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  char* act0 = scratch;
+  char* act1 = scratch + d.scratch_bytes(rows) / 2;
   const char* in = x;
   for (size_t l = 0; l < d.layers.size(); ++l) {
     const DenseLayer& L = d.layers[l];
@@ -476,7 +512,7 @@ static size_t row_out_bytes(const ModelDesc& d) { return d.tmpl == Template::Aff
 bool Node::ensure_slot(Slot* s, const ModelDesc& d, int64_t rows, std::string* err) {
   int64_t cap_rows = rows > cfg_.max_batch ? rows : cfg_.max_batch;
   size_t io = (size_t)cap_rows * std::max(row_in_bytes(d), row_out_bytes(d));
-  size_t act = (size_t)cap_rows * (size_t)std::max(d.max_width, 1) * 4;
+  size_t act = d.scratch_bytes(cap_rows);
   size_t ws = model_ws_bytes(d);
   if (io > s->io_cap) {
     cudaStreamSynchronize(compute_);
@@ -492,15 +528,13 @@ bool Node::ensure_slot(Slot* s, const ModelDesc& d, int64_t rows, std::string* e
     CU_OK(cudaMalloc((void**)&s->d_out, io), err, false);
     s->io_cap = io;
   }
-  if (act > s->act_cap) {
+  if (act > s->scratch_cap) {
     cudaStreamSynchronize(compute_);
-    if (s->act0) cudaFree(s->act0);
-    if (s->act1) cudaFree(s->act1);
-    s->act0 = s->act1 = nullptr;
-    s->act_cap = 0;
-    CU_OK(cudaMalloc((void**)&s->act0, act), err, false);
-    CU_OK(cudaMalloc((void**)&s->act1, act), err, false);
-    s->act_cap = act;
+    if (s->scratch) cudaFree(s->scratch);
+    s->scratch = nullptr;
+    s->scratch_cap = 0;
+    CU_OK(cudaMalloc((void**)&s->scratch, act), err, false);
+    s->scratch_cap = act;
   }
   if (ws > s->ws_cap) {
     cudaStreamSynchronize(compute_);
@@ -636,7 +670,7 @@ void Node::batcher_loop() {
       if (e == cudaSuccess) e = cudaEventRecord(s->in_done, in_);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(compute_, s->in_done, 0);
       if (e == cudaSuccess && !dm->ready_seen) e = cudaStreamWaitEvent(compute_, dm->ready, 0);
-      if (e == cudaSuccess) e = run_model(*dm, s->d_in, rows, s->d_out, s->act0, s->act1, s->ws, s->ws_cap, compute_);
+      if (e == cudaSuccess) e = run_model(*dm, s->d_in, rows, s->d_out, s->scratch, s->ws, s->ws_cap, compute_);
       if (e == cudaSuccess) e = cudaEventRecord(s->k_done, compute_);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(out_, s->k_done, 0);
       if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_out, s->d_out, (size_t)rows * rout, cudaMemcpyDeviceToHost, out_);
@@ -734,8 +768,8 @@ int Node::predict_device(const ModelId& id, const void* x, int64_t rows, void* y
   const ModelDesc& d = dm->desc;
   cudaError_t e = cudaSuccess;
   StreamScratch* sc = nullptr;
-  if (d.tmpl == Template::Mlp) {
-    const size_t act = (((size_t)rows * d.max_width * 4) + 255) & ~(size_t)255;
+  if (d.tmpl != Template::Affine) {
+    const size_t act = d.scratch_bytes(rows);
     const size_t ws = model_ws_bytes(d);
     std::lock_guard<std::mutex> lk(scratch_mu_);
     sc = &stream_scratch_[st];
@@ -746,8 +780,8 @@ int Node::predict_device(const ModelId& id, const void* x, int64_t rows, void* y
         sc->base = nullptr;
       }
       size_t a = act > sc->act_bytes ? act : sc->act_bytes, w = ws > sc->ws_bytes ? ws : sc->ws_bytes;
-      e = cudaMalloc((void**)&sc->base, 2 * a + w);
-      if (e == cudaSuccess) e = cudaMemsetAsync(sc->base + 2 * a, 0, w, st);
+      e = cudaMalloc((void**)&sc->base, a + w);
+      if (e == cudaSuccess) e = cudaMemsetAsync(sc->base + a, 0, w, st);
       sc->act_bytes = a;
       sc->ws_bytes = w;
     }
@@ -755,9 +789,8 @@ int Node::predict_device(const ModelId& id, const void* x, int64_t rows, void* y
   if (e == cudaSuccess && !dm->ready_seen) e = cudaStreamWaitEvent(st, dm->ready, 0);
   if (e == cudaSuccess) {
     char* a0 = sc ? sc->base : nullptr;
-    char* a1 = sc ? sc->base + sc->act_bytes : nullptr;
-    void* ws = sc ? sc->base + 2 * sc->act_bytes : nullptr;
-    e = run_model(*dm, (const char*)x, rows, (char*)y, a0, a1, ws, sc ? sc->ws_bytes : 0, st);
+    void* ws = sc ? sc->base + sc->act_bytes : nullptr;
+    e = run_model(*dm, (const char*)x, rows, (char*)y, a0, ws, sc ? sc->ws_bytes : 0, st);
   }
   if (e == cudaSuccess) e = cudaEventRecord(ev, st);
   {

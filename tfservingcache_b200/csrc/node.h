@@ -91,9 +91,9 @@ class Node {
 
  private:
   struct Slot {
-    char *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *act0 = nullptr, *act1 = nullptr;
+    char *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *scratch = nullptr;
     void* ws = nullptr;
-    size_t io_cap = 0, act_cap = 0, ws_cap = 0;
+    size_t io_cap = 0, scratch_cap = 0, ws_cap = 0;
     cudaEvent_t in_done = nullptr, k_done = nullptr, done = nullptr;
     std::vector<PredictRequest*> reqs;
     std::shared_ptr<DeviceModel> dm;
@@ -103,7 +103,7 @@ class Node {
     cudaEvent_t ev;
     std::shared_ptr<DeviceModel> dm;
   };
-  struct StreamScratch {  // activation ping-pong + split-K workspace of one caller stream
+  struct StreamScratch {  // activation buffers + split-K workspace of one caller stream
     char* base = nullptr;
     size_t act_bytes = 0, ws_bytes = 0;
   };
@@ -118,8 +118,8 @@ class Node {
   void refresh_state_locked(DeviceModel* d);
   void* host_alloc(size_t bytes, std::function<void(void*, size_t)>* release);
   bool ensure_slot(Slot* s, const ModelDesc& d, int64_t rows, std::string* err);
-  cudaError_t run_model(const DeviceModel& dm, const char* x, int64_t rows, char* y, char* act0, char* act1, void* ws,
-                        size_t ws_cap, cudaStream_t st);
+  cudaError_t run_model(const DeviceModel& dm, const char* x, int64_t rows, char* y, char* scratch, void* ws, size_t ws_cap,
+                        cudaStream_t st);
   static size_t model_ws_bytes(const ModelDesc& d);
   void batcher_loop();
   void completer_loop();

@@ -169,7 +169,15 @@ SyntheticModelProvider::SyntheticModelProvider(const Json& cfg) {
   count_ = cfg.get_int("modelProvider.synthetic.count", 1000);
   seed_base_ = cfg.get_int("modelProvider.synthetic.seedBase", 1000);
   threads_ = (int)cfg.get_int("modelProvider.synthetic.threads", std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
-  if (tmpl == "affine") {
+  if (tmpl == "manifest") {
+    // any "tfsc-b200-v1" manifest (e.g. the ResNet-50 graph built by modelformat.resnet50_manifest()):
+    // weights are synthesized per op, tensor id 2*i (kernel, uniform with variance 1/fan_in) and 2*i+1 (bias)
+    std::string err;
+    const Json* m = cfg.get("modelProvider.synthetic.manifest");
+    if (!m || !parse_manifest(*m, &desc_, &err)) {
+      bad_ = "modelProvider.synthetic.manifest: " + (m ? err : std::string("missing"));
+    }
+  } else if (tmpl == "affine") {
     desc_ = make_affine_desc();
     affine_a_ = cfg.get_num("modelProvider.synthetic.a", 0.5);
     affine_b_ = cfg.get_num("modelProvider.synthetic.b", 2.0);
@@ -193,6 +201,10 @@ bool SyntheticModelProvider::index_of(const std::string& name, int64_t* j) const
 
 int64_t SyntheticModelProvider::model_size(const std::string& name, int64_t version, std::string* err) {
   int64_t j;
+  if (!bad_.empty()) {
+    *err = bad_;
+    return -1;
+  }
   if (!index_of(name, &j) || version < 1) {
     *err = "No matching model found";
     return -1;
@@ -222,6 +234,17 @@ std::shared_ptr<HostModel> SyntheticModelProvider::load_model(const std::string&
     memset(m->data, 0, m->bytes);
     base[desc_.a_off / 4] = (float)affine_a_;
     base[desc_.b_off / 4] = (float)affine_b_;
+    return m;
+  }
+  if (desc_.tmpl == Template::Graph) {
+    memset(m->data, 0, m->bytes);
+    for (size_t i = 0; i < desc_.ops.size(); ++i) {
+      const GraphOp& o = desc_.ops[i];
+      if (o.kind != OpKind::Conv && o.kind != OpKind::Dense) continue;
+      const uint64_t fan_in = (uint64_t)o.kh * o.kw * o.c;
+      fill(base + o.w_off / 4, seed, (uint32_t)(2 * i), fan_in * o.cout, (float)std::sqrt(3.0 / (double)fan_in), threads_);
+      fill(base + o.b_off / 4, seed, (uint32_t)(2 * i + 1), (uint64_t)o.cout, 0.1f, 1);
+    }
     return m;
   }
   for (size_t l = 0; l < desc_.layers.size(); ++l) {

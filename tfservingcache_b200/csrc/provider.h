@@ -57,6 +57,7 @@ class SyntheticModelProvider : public ModelProvider {
   int64_t count_ = 0, seed_base_ = 1000;
   double affine_a_ = 0.5, affine_b_ = 2.0;
   int threads_ = 8;
+  std::string bad_;  // configuration error reported on first use
 };
 
 std::unique_ptr<ModelProvider> create_provider(const Json& cfg, std::string* err);  // main.go:152-185

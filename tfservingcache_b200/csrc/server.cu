@@ -242,6 +242,12 @@ static int resolve(tfsc_server* s, const std::string& name, const std::string& v
 static void out_shape(const ModelDesc& d, int64_t rows, const std::vector<int64_t>& in_shape, std::vector<int64_t>* shape) {
   if (d.tmpl == Template::Affine) {
     *shape = in_shape;
+  } else if (d.tmpl == Template::Graph) {
+    // [B, H, W, C] -> [B, classes]: batch dims are whatever precedes the per-image input shape
+    shape->clear();
+    if (in_shape.size() > d.input_shape.size())
+      for (size_t i = 0; i + d.input_shape.size() < in_shape.size(); ++i) shape->push_back(in_shape[i]);
+    for (auto v : d.output_shape) shape->push_back(v);
   } else {
     shape->clear();
     // leading dims of the input are kept ([B, in] -> [B, out]; [in] -> [out])
@@ -653,6 +659,31 @@ int tfsc_k_dense_tc(const float* x, const float* w, const float* b, float* y, in
     return fail(TFSC_E_INVALID, "dense_tc: unsupported shape/alignment (rows<=64, n%%32==0, k%%4==0, 16B-aligned)");
   cudaError_t e = launch_dense_tc(x, w, b, y, rows, k, n, relu != 0, workspace, workspace_bytes, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "dense_tc: %s", cudaGetErrorString(e));
+}
+
+int tfsc_k_gemm(const float* a, const float* b, const float* bias, const float* r, float* c, int m, int n, int k, int lda,
+                int act, void* stream) {
+  if (int rc = check_device()) return rc;
+  cudaError_t e = launch_gemm(a, b, bias, r, c, m, n, k, lda, act, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "gemm: %s", cudaGetErrorString(e));
+}
+int tfsc_k_im2col(const float* x, float* col, int batch, int h, int w, int c, int kh, int kw, int stride, int pad, int ldc,
+                  void* stream) {
+  if (int rc = check_device()) return rc;
+  const int oh = (h + 2 * pad - kh) / stride + 1, ow = (w + 2 * pad - kw) / stride + 1;
+  cudaError_t e = launch_im2col(x, col, batch, h, w, c, kh, kw, stride, pad, oh, ow, ldc, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "im2col: %s", cudaGetErrorString(e));
+}
+int tfsc_k_maxpool(const float* x, float* y, int batch, int h, int w, int c, int kh, int kw, int stride, int pad, void* stream) {
+  if (int rc = check_device()) return rc;
+  const int oh = (h + 2 * pad - kh) / stride + 1, ow = (w + 2 * pad - kw) / stride + 1;
+  cudaError_t e = launch_maxpool(x, y, batch, h, w, c, kh, kw, stride, pad, oh, ow, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "maxpool: %s", cudaGetErrorString(e));
+}
+int tfsc_k_avgpool(const float* x, float* y, int batch, int hw, int c, void* stream) {
+  if (int rc = check_device()) return rc;
+  cudaError_t e = launch_avgpool(x, y, batch, hw, c, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "avgpool: %s", cudaGetErrorString(e));
 }
 
 }  // extern "C"

@@ -51,3 +51,56 @@ def _write(version_dir: str, man: dict, blob: np.ndarray):
     with open(os.path.join(version_dir, "tfsc_model.json"), "w") as f:
         json.dump(man, f)
     blob.astype("<f4").tofile(os.path.join(version_dir, "weights.bin"))
+
+
+def _graph_manifest(input_shape, ops, n_buffers, input_name="x", output_name="y"):
+    off = 0
+    for op in ops:
+        if op["op"] in ("conv", "dense"):
+            k = op.get("kh", 1) * op.get("kw", 1) * op["c"]
+            op["w_offset"] = off
+            off = _align256(off + k * op["cout"] * 4)
+            op["b_offset"] = off
+            off = _align256(off + op["cout"] * 4)
+    return {"format": "tfsc-b200-v1", "template": "graph", "dtype": "float32",
+            "signature": {"input": input_name, "output": output_name}, "input_shape": list(input_shape),
+            "n_buffers": n_buffers, "ops": ops, "weights_bytes": off}
+
+
+def resnet50_manifest(image=224, classes=1000, width=64, blocks=(3, 4, 6, 3)):
+    """ResNet-50 v1.5 (torchvision topology: stride on the 3x3 conv) as a graph bundle, NHWC, BatchNorm folded into
+    kernel + bias. Buffers: 0 = block input / identity, 1 = 1x1 out, 2 = 3x3 out, 3 = block out, 4 = downsample."""
+    ops, h = [], image
+    ops.append({"op": "conv", "src": -1, "dst": 0, "h": h, "w": h, "c": 3, "kh": 7, "kw": 7, "stride": 2, "pad": 3,
+                "cout": width, "act": "relu"})
+    h = (h + 6 - 7) // 2 + 1
+    ops.append({"op": "maxpool", "src": 0, "dst": 1, "h": h, "w": h, "c": width, "kh": 3, "kw": 3, "stride": 2, "pad": 1})
+    h = (h + 2 - 3) // 2 + 1
+    cur, cin = 1, width          # `cur` = buffer holding the block input
+    free = [0, 2, 3, 4]
+    for li, nb in enumerate(blocks):
+        planes = width * (2 ** li)
+        for bi in range(nb):
+            stride = 2 if (bi == 0 and li > 0) else 1
+            a, b, c_, d = [x for x in range(5) if x != cur][:4]
+            ho = (h + 2 - 3) // stride + 1
+            ops.append({"op": "conv", "src": cur, "dst": a, "h": h, "w": h, "c": cin, "kh": 1, "kw": 1, "stride": 1, "pad": 0,
+                        "cout": planes, "act": "relu"})
+            ops.append({"op": "conv", "src": a, "dst": b, "h": h, "w": h, "c": planes, "kh": 3, "kw": 3, "stride": stride,
+                        "pad": 1, "cout": planes, "act": "relu"})
+            ident = cur
+            if bi == 0:  # projection shortcut
+                ops.append({"op": "conv", "src": cur, "dst": c_, "h": h, "w": h, "c": cin, "kh": 1, "kw": 1, "stride": stride,
+                            "pad": 0, "cout": planes * 4, "act": "none"})
+                ident = c_
+            ops.append({"op": "conv", "src": b, "dst": d, "res": ident, "h": ho, "w": ho, "c": planes, "kh": 1, "kw": 1,
+                        "stride": 1, "pad": 0, "cout": planes * 4, "act": "relu"})
+            cur, cin, h = d, planes * 4, ho
+    a = [x for x in range(5) if x != cur][0]
+    ops.append({"op": "avgpool", "src": cur, "dst": a, "h": h, "w": h, "c": cin})
+    ops.append({"op": "dense", "src": a, "dst": -2, "h": 1, "w": 1, "c": cin, "cout": classes, "act": "none"})
+    return _graph_manifest([image, image, 3], ops, 5)
+
+
+def write_graph_bundle(version_dir: str, manifest: dict, blob: np.ndarray):
+    _write(version_dir, manifest, np.asarray(blob, np.float32))
