@@ -166,7 +166,7 @@ def resnet50_ops(image=224, classes=1000):
     return ops
 
 
-def graph_manifest(input_shape, ops, n_buffers=5):
+def graph_manifest(input_shape, ops, n_buffers=5, signature=("x", "y"), input_dtype="float32"):
     off = 0
     for o in ops:
         if o["op"] in ("conv", "dense"):
@@ -175,21 +175,66 @@ def graph_manifest(input_shape, ops, n_buffers=5):
             off = align256(off + k * o["cout"] * 4)
             o["b_offset"] = off
             off = align256(off + o["cout"] * 4)
-    return {"format": "tfsc-b200-v1", "template": "graph", "dtype": "float32", "signature": {"input": "x", "output": "y"},
+        elif o["op"] in ("layernorm", "embed"):
+            o["w_offset"] = off
+            off = align256(off + o["c"] * 4)
+            o["b_offset"] = off
+            off = align256(off + o["c"] * 4)
+            if o["op"] == "embed":
+                o["word_offset"] = off
+                off = align256(off + o["vocab"] * o["c"] * 4)
+                o["pos_offset"] = off
+                off = align256(off + o["max_pos"] * o["c"] * 4)
+                o["type_offset"] = off
+                off = align256(off + 2 * o["c"] * 4)
+    return {"format": "tfsc-b200-v1", "template": "graph", "dtype": "float32", "input_dtype": input_dtype,
+            "signature": {"input": signature[0], "output": signature[1]},
             "input_shape": list(input_shape), "n_buffers": n_buffers, "ops": ops, "weights_bytes": off}
 
 
+EMBED_SCALE = float(np.float32(0.05))
+
+
 def synth_graph_blob(man: dict, seed: int) -> np.ndarray:
+    """Tensor ids of op i: 8*i + {0 kernel / gamma, 1 bias / beta, 2 word, 3 pos, 4 type}."""
     blob = np.zeros(man["weights_bytes"] // 4, dtype=np.float32)
+
+    def put(off, arr):
+        blob[off // 4: off // 4 + arr.size] = arr
+
     for i, o in enumerate(man["ops"]):
-        if o["op"] not in ("conv", "dense"):
-            continue
-        fan_in = o.get("kh", 1) * o.get("kw", 1) * o["c"]
-        w = synth_tensor(seed, 2 * i, fan_in * o["cout"], weight_scale(fan_in))
-        b = synth_tensor(seed, 2 * i + 1, o["cout"], BIAS_SCALE)
-        blob[o["w_offset"] // 4: o["w_offset"] // 4 + w.size] = w
-        blob[o["b_offset"] // 4: o["b_offset"] // 4 + b.size] = b
+        if o["op"] in ("conv", "dense"):
+            fan_in = o.get("kh", 1) * o.get("kw", 1) * o["c"]
+            put(o["w_offset"], synth_tensor(seed, 8 * i, fan_in * o["cout"], weight_scale(fan_in)))
+            put(o["b_offset"], synth_tensor(seed, 8 * i + 1, o["cout"], BIAS_SCALE))
+        elif o["op"] in ("layernorm", "embed"):
+            put(o["w_offset"], synth_tensor(seed, 8 * i, o["c"], BIAS_SCALE) + np.float32(1.0))
+            put(o["b_offset"], synth_tensor(seed, 8 * i + 1, o["c"], BIAS_SCALE))
+            if o["op"] == "embed":
+                put(o["word_offset"], synth_tensor(seed, 8 * i + 2, o["vocab"] * o["c"], EMBED_SCALE))
+                put(o["pos_offset"], synth_tensor(seed, 8 * i + 3, o["max_pos"] * o["c"], EMBED_SCALE))
+                put(o["type_offset"], synth_tensor(seed, 8 * i + 4, 2 * o["c"], EMBED_SCALE))
     return blob
+
+
+def bert_ops(seq=128, hidden=768, layers=12, heads=12, inter=3072, vocab=30522, max_pos=512, labels=2):
+    """Independent restatement of BERT-base (Devlin et al. 2018; google-research/bert modeling.py structure:
+    embeddings + LayerNorm, L x [self-attention, add & norm, GELU feed-forward, add & norm], tanh pooler on the
+    first token, linear classifier) in the bundle's op list."""
+    def lin(src, dst, cin, cout, act="none"):
+        return dict(op="conv", src=src, dst=dst, h=seq, w=1, c=cin, kh=1, kw=1, stride=1, pad=0, cout=cout, act=act)
+    ops = [dict(op="embed", src=-1, dst=0, h=seq, w=1, c=hidden, vocab=vocab, max_pos=max_pos, eps=1e-12)]
+    for _layer in range(layers):
+        ops.append(lin(0, 1, hidden, 3 * hidden))
+        ops.append(dict(op="attention", src=1, dst=2, h=seq, w=1, c=3 * hidden, heads=heads))
+        ops.append(lin(2, 3, hidden, hidden))
+        ops.append(dict(op="layernorm", src=3, res=0, dst=2, h=seq, w=1, c=hidden, eps=1e-12))
+        ops.append(lin(2, 1, hidden, inter, "gelu"))
+        ops.append(lin(1, 3, inter, hidden))
+        ops.append(dict(op="layernorm", src=3, res=2, dst=0, h=seq, w=1, c=hidden, eps=1e-12))
+    ops.append(dict(op="dense", src=0, dst=1, h=1, w=1, c=hidden, cout=hidden, act="tanh"))
+    ops.append(dict(op="dense", src=1, dst=-2, h=1, w=1, c=hidden, cout=labels, act="none"))
+    return ops
 
 
 def graph_forward(man: dict, blob: np.ndarray, x: np.ndarray, dtype=np.float64) -> np.ndarray:
@@ -199,16 +244,53 @@ def graph_forward(man: dict, blob: np.ndarray, x: np.ndarray, dtype=np.float64) 
     import torch.nn.functional as F
     td = torch.float64 if dtype == np.float64 else torch.float32
     ish = man["input_shape"]
-    xb = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).reshape(-1, *ish).to(td)
-    bufs = {-1: xb.permute(0, 3, 1, 2).contiguous()}
+    is_ids = man.get("input_dtype", "float32") == "int32"
+    if is_ids:
+        ids = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).reshape(-1, *ish)
+        bufs = {-1: ids}
+    else:
+        xb = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).reshape(-1, *ish).to(td)
+        bufs = {-1: xb.permute(0, 3, 1, 2).contiguous()}
+
+    def vec(off, n):
+        return torch.from_numpy(blob[off // 4: off // 4 + n]).to(td)
+
+    def layer_norm(v, o):  # v: [B, C, S, 1]
+        mean = v.mean(dim=1, keepdim=True)
+        var = ((v - mean) ** 2).mean(dim=1, keepdim=True)
+        g, bta = vec(o["w_offset"], o["c"]).view(1, -1, 1, 1), vec(o["b_offset"], o["c"]).view(1, -1, 1, 1)
+        return (v - mean) / torch.sqrt(var + o.get("eps", 1e-12)) * g + bta
+
     for o in man["ops"]:
         src = bufs[o["src"]]
-        if o["op"] in ("conv", "dense"):
+        if o["op"] == "embed":
+            S, Hd = o["h"], o["c"]
+            word = vec(o["word_offset"], o["vocab"] * Hd).view(o["vocab"], Hd)
+            pos = vec(o["pos_offset"], o["max_pos"] * Hd).view(o["max_pos"], Hd)[:S]
+            typ = vec(o["type_offset"], 2 * Hd).view(2, Hd)[0]
+            e = word[src.clamp(0, o["vocab"] - 1)] + pos.unsqueeze(0) + typ          # [B, S, H]
+            y = layer_norm(e.permute(0, 2, 1).unsqueeze(-1), o)
+        elif o["op"] == "layernorm":
+            v = src + (bufs[o["res"]] if o.get("res", -100) != -100 else 0)
+            y = layer_norm(v, o)
+        elif o["op"] == "attention":
+            Bn, C3, S, _ = src.shape
+            Hd, nh = C3 // 3, o["heads"]
+            dh = Hd // nh
+            qkv = src.squeeze(-1).permute(0, 2, 1)                                    # [B, S, 3H]
+            q, k, v = (qkv[..., i * Hd:(i + 1) * Hd].reshape(Bn, S, nh, dh).permute(0, 2, 1, 3) for i in range(3))
+            sc = q @ k.transpose(-1, -2) / math.sqrt(dh)
+            mask = (bufs[-1] == 0).to(td) * -10000.0                                  # [B, S] additive, [PAD] = 0
+            p = torch.softmax(sc + mask[:, None, None, :], dim=-1)
+            ctx = (p @ v).permute(0, 2, 1, 3).reshape(Bn, S, Hd)
+            y = ctx.permute(0, 2, 1).unsqueeze(-1)
+        elif o["op"] in ("conv", "dense"):
             kh, kw, c, cout = o.get("kh", 1), o.get("kw", 1), o["c"], o["cout"]
             w = torch.from_numpy(blob[o["w_offset"] // 4: o["w_offset"] // 4 + kh * kw * c * cout].reshape(kh, kw, c, cout)).to(td)
             b = torch.from_numpy(blob[o["b_offset"] // 4: o["b_offset"] // 4 + cout]).to(td)
             if o["op"] == "dense":
-                y = src.reshape(src.shape[0], -1) @ w.reshape(c, cout) + b
+                flat = src.permute(0, 2, 3, 1).reshape(src.shape[0], -1)[:, :c]      # first token / the whole vector
+                y = flat @ w.reshape(c, cout) + b
                 y = y.reshape(src.shape[0], cout, 1, 1)
             else:
                 y = F.conv2d(src, w.permute(3, 2, 0, 1).contiguous(), b, stride=o["stride"], padding=o["pad"])
@@ -218,6 +300,8 @@ def graph_forward(man: dict, blob: np.ndarray, x: np.ndarray, dtype=np.float64) 
                 y = torch.relu(y)
             elif o.get("act") == "gelu":
                 y = F.gelu(y)
+            elif o.get("act") == "tanh":
+                y = torch.tanh(y)
         elif o["op"] == "maxpool":
             y = F.max_pool2d(src, (o["kh"], o["kw"]), stride=o["stride"], padding=o["pad"])
         elif o["op"] == "avgpool":

@@ -116,3 +116,48 @@ def test_resnet50_full_size_matches_oracle_and_rest():
     ref = models.graph_forward(oman, models.synth_graph_blob(oman, 1001), x, np.float64)
     assert y.shape == (2, 1000) and _err(y, ref) <= TOL
     assert st["h2d_weight_bytes"] == 102121984
+
+
+# ---- X5: transformer ops / BERT bundle -------------------------------------------------------------------
+def test_small_bert_through_server_grpc_and_rest_matches_oracle():
+    _torch()
+    import json
+    from oracle import wire
+    args = dict(seq=16, hidden=64, layers=2, heads=4, inter=128, vocab=100, max_pos=32, labels=3)
+    man = t.modelformat.bert_manifest(**args)
+    oman = models.graph_manifest([16], models.bert_ops(**args), 4, ("input_ids", "logits"), "int32")
+    rng = np.random.default_rng(0)
+    with _server(man, arena=64 << 20) as srv:
+        for j, bsz in [(1, 1), (2, 4)]:
+            ids = rng.integers(1, 100, (bsz, 16)).astype(np.int32)
+            ids[-1, 9:] = 0                                   # [PAD] tail -> masked keys
+            y = srv.predict(f"m{j}", "1", ids)
+            ref = models.graph_forward(oman, models.synth_graph_blob(oman, 1000 + j), ids, np.float64)
+            assert y.shape == (bsz, 3) and _err(y, ref) <= TOL
+        # float ids are a signature error; gRPC int_val and tensor_content both work; REST resolves ints from JSON
+        with pytest.raises(t._lib.TfscError) as e:
+            srv.predict("m1", "1", ids.astype(np.float32))
+        assert e.value.code == t._lib.E_INVALID
+        ref = models.graph_forward(oman, models.synth_graph_blob(oman, 1001), ids, np.float64)
+        for use_content in (True, False):
+            req = wire.encode_predict_request("m1", 1, {"input_ids": ids}, use_content=use_content)
+            _spec, outs = wire.decode_predict_response(srv.grpc_predict(req))
+            assert _err(outs["logits"], ref) <= TOL
+        st, body = srv.rest_handle("POST", "/v1/models/m1/versions/1:predict", json.dumps({"instances": ids.tolist()}).encode())
+        assert st == 200 and _err(np.array(json.loads(body)["predictions"]), ref) <= TOL
+
+
+def test_bert_base_full_size_matches_oracle():
+    """BASELINE configs[3] model: BERT-base (L12/H768/A12, vocab 30522, 109.5 M parameters = 438 MB), batch 8 x 128."""
+    _torch()
+    man = t.modelformat.bert_manifest()
+    oman = models.graph_manifest([128], models.bert_ops(), 4, ("input_ids", "logits"), "int32")
+    assert man["weights_bytes"] == oman["weights_bytes"] == 437935360
+    rng = np.random.default_rng(2)
+    ids = rng.integers(1, 30522, (8, 128)).astype(np.int32)
+    ids[3, 100:] = 0
+    ids[7, 5:] = 0
+    with _server(man, arena=1 << 30, count=4) as srv:
+        y = srv.predict("m2", "1", ids)
+    ref = models.graph_forward(oman, models.synth_graph_blob(oman, 1002), ids, np.float64)
+    assert y.shape == (8, 2) and _err(y, ref) <= TOL

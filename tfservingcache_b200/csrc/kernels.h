@@ -33,6 +33,12 @@ cudaError_t launch_im2col(const float* x, float* col, int Bn, int H, int W, int 
 cudaError_t launch_maxpool(const float* x, float* y, int Bn, int H, int W, int C, int KH, int KW, int stride, int pad, int OH,
                            int OW, cudaStream_t s);
 cudaError_t launch_avgpool(const float* x, float* y, int Bn, int HW, int C, cudaStream_t s);
+// y = LayerNorm(x (+res)) or, with ids != nullptr, LayerNorm(word[id] + pos[s] + type[0]) (BERT embeddings)
+cudaError_t launch_layernorm(const float* x, const float* res, const int* ids, const float* word, const float* pos,
+                             const float* type, const float* gamma, const float* beta, float* y, int tokens, int S, int H,
+                             int vocab, float eps, cudaStream_t s);
+cudaError_t launch_attention(const float* qkv, const int* ids, float* ctx, int Bn, int S, int H, int heads, cudaStream_t s);
+size_t attention_smem_bytes(int S, int H, int heads);
 
 int64_t kernel_launch_count();
 

@@ -127,6 +127,7 @@ bool parse_manifest(const Json& j, ModelDesc* d, std::string* err) {
       return false;
     }
     for (auto& v : ish->arr) d->input_shape.push_back(v.integer());
+    d->input_dtype = j.get_str("input_dtype", "float32") == "int32" ? TFSC_DT_INT32 : TFSC_DT_FLOAT;
     d->n_buffers = (int)j.get_int("n_buffers", 0);
     if (d->n_buffers < 1 || d->n_buffers > 16) {
       *err = "graph manifest: n_buffers out of range";
@@ -143,6 +144,9 @@ bool parse_manifest(const Json& j, ModelDesc* d, std::string* err) {
       else if (kind == "maxpool") o.kind = OpKind::MaxPool;
       else if (kind == "avgpool") o.kind = OpKind::AvgPool;
       else if (kind == "dense") o.kind = OpKind::Dense;
+      else if (kind == "embed") o.kind = OpKind::Embed;
+      else if (kind == "layernorm") o.kind = OpKind::LayerNorm;
+      else if (kind == "attention") o.kind = OpKind::Attention;
       else {
         *err = "graph manifest: unknown op '" + kind + "'";
         return false;
@@ -159,14 +163,33 @@ bool parse_manifest(const Json& j, ModelDesc* d, std::string* err) {
       o.pad = (int)oj.get_int("pad", 0);
       o.cout = (int)oj.get_int("cout", o.c);
       const std::string act = oj.get_str("act", "none");
-      o.act = act == "relu" ? 1 : act == "gelu" ? 2 : 0;
+      o.act = act == "relu" ? 1 : act == "gelu" ? 2 : act == "tanh" ? 3 : 0;
+      o.heads = (int)oj.get_int("heads", 1);
+      o.vocab = (int)oj.get_int("vocab", 0);
+      o.max_pos = (int)oj.get_int("max_pos", 0);
+      o.word_off = (size_t)oj.get_int("word_offset", 0);
+      o.pos_off = (size_t)oj.get_int("pos_offset", 0);
+      o.type_off = (size_t)oj.get_int("type_offset", 0);
+      o.eps = (float)oj.get_num("eps", 1e-12);
       o.w_off = (size_t)oj.get_int("w_offset", 0);
       o.b_off = (size_t)oj.get_int("b_offset", 0);
       if (o.h < 1 || o.w < 1 || o.c < 1 || o.kh < 1 || o.kw < 1 || o.stride < 1 || o.pad < 0 || o.cout < 1) {
         *err = "graph manifest: bad op geometry";
         return false;
       }
-      if (o.kind == OpKind::AvgPool) {
+      if (o.kind == OpKind::Embed || o.kind == OpKind::LayerNorm) {
+        o.oh = o.h;
+        o.ow = o.w;
+        o.cout = o.c;
+      } else if (o.kind == OpKind::Attention) {
+        o.oh = o.h;
+        o.ow = o.w;
+        o.cout = o.c / 3;
+        if (o.c % 3 || o.heads < 1 || o.cout % o.heads || o.w != 1) {
+          *err = "graph manifest: attention expects a packed [S,1,3H] qkv source";
+          return false;
+        }
+      } else if (o.kind == OpKind::AvgPool) {
         o.oh = o.ow = 1;
         o.cout = o.c;
       } else if (o.kind == OpKind::Dense) {
@@ -177,7 +200,8 @@ bool parse_manifest(const Json& j, ModelDesc* d, std::string* err) {
         o.ow = (o.w + 2 * o.pad - o.kw) / o.stride + 1;
         if (o.kind == OpKind::MaxPool) o.cout = o.c;
       }
-      const int64_t in_e = (int64_t)o.h * o.w * o.c, out_e = (int64_t)o.oh * o.ow * o.cout;
+      const int64_t in_e = o.kind == OpKind::Embed ? (int64_t)o.h * o.w : (int64_t)o.h * o.w * o.c;
+      const int64_t out_e = (int64_t)o.oh * o.ow * o.cout;
       auto buf_ok = [&](int b) { return b == -1 || (b >= 0 && b < d->n_buffers); };
       if (!buf_ok(o.src) || !(o.dst == -2 || (o.dst >= 0 && o.dst < d->n_buffers)) || (o.res != -100 && !buf_ok(o.res)) ||
           o.dst == o.src || o.dst == o.res) {
@@ -185,7 +209,21 @@ bool parse_manifest(const Json& j, ModelDesc* d, std::string* err) {
         return false;
       }
       const int64_t have = o.src == -1 ? in_elems : written[o.src];
-      if (have != in_e || (o.res != -100 && (o.res == -1 ? in_elems : written[o.res]) != out_e)) {
+      o.lda = have;
+      const bool size_ok = o.kind == OpKind::Dense ? have >= in_e : have == in_e;  // Dense may read the first token only
+      if (o.kind == OpKind::Embed && (o.src != -1 || o.vocab < 1 || o.max_pos < o.h || (o.word_off & 255) || (o.pos_off & 255) ||
+                                      (o.type_off & 255) || o.word_off + (size_t)o.vocab * o.c * 4 > d->weights_bytes ||
+                                      o.pos_off + (size_t)o.max_pos * o.c * 4 > d->weights_bytes ||
+                                      o.type_off + (size_t)2 * o.c * 4 > d->weights_bytes)) {
+        *err = "graph manifest: bad embed op";
+        return false;
+      }
+      if ((o.kind == OpKind::Embed || o.kind == OpKind::LayerNorm) &&
+          ((o.w_off & 255) || (o.b_off & 255) || o.w_off + (size_t)o.c * 4 > d->weights_bytes || o.b_off + (size_t)o.c * 4 > d->weights_bytes)) {
+        *err = "graph manifest: LayerNorm gamma/beta out of range";
+        return false;
+      }
+      if (!size_ok || (o.res != -100 && (o.res == -1 ? in_elems : written[o.res]) != out_e)) {
         *err = "graph manifest: op input size does not match its producer";
         return false;
       }

@@ -17,14 +17,19 @@ enum class Template { Affine, Mlp, Graph };
 // One node of a "graph" bundle (conv nets): activations are NHWC fp32, `src`/`dst`/`res` index scratch
 // activation buffers (-1 = the request tensor, -2 = the response tensor). Weights: conv/dense kernel
 // flattened to [kh*kw*c, cout] row-major (= TF HWIO / dense layout) at w_off, bias (folded BN) at b_off.
-enum class OpKind { Conv, MaxPool, AvgPool, Dense };
+enum class OpKind { Conv, MaxPool, AvgPool, Dense, Embed, LayerNorm, Attention };
 struct GraphOp {
   OpKind kind = OpKind::Conv;
   int src = -1, dst = 0, res = -100;  // res = -100: no residual input
   int h = 1, w = 1, c = 1;            // input H, W, C per image
   int kh = 1, kw = 1, stride = 1, pad = 0, cout = 1, oh = 1, ow = 1;
-  int act = 0;                        // 0 none, 1 relu, 2 gelu
-  size_t w_off = 0, b_off = 0;
+  int act = 0;                        // 0 none, 1 relu, 2 gelu(erf), 3 tanh
+  size_t w_off = 0, b_off = 0;        // kernel / bias; LayerNorm + Embed: gamma / beta
+  // transformer ops (a "image" is a sequence: h = S tokens, w = 1, c = hidden width)
+  int heads = 1, vocab = 0, max_pos = 0;
+  size_t word_off = 0, pos_off = 0, type_off = 0;  // Embed tables [vocab,c], [max_pos,c], [2,c]
+  float eps = 1e-12f;
+  int64_t lda = 0;                    // Dense: elements per image of the source (> c selects the first token)
 };
 
 struct DenseLayer {
@@ -49,6 +54,7 @@ struct ModelDesc {
   int64_t col_elems = 0;  // largest im2col matrix, elements per image
   std::vector<int64_t> input_shape;   // per image, e.g. [224,224,3]
   std::vector<int64_t> output_shape;  // per image, e.g. [1000]
+  int input_dtype = TFSC_DT_FLOAT;    // TFSC_DT_INT32 for token-id inputs (BERT)
   // bytes of executor scratch (activation buffers + im2col) for `rows` images / batch rows
   size_t scratch_bytes(int64_t rows) const;
 };

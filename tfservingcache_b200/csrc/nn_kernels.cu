@@ -126,6 +126,7 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, const 
       if (R) v += __ldg(R + (size_t)gm * N + gn);
       if (act == 1) v = fmaxf(v, 0.f);
       else if (act == 2) v = gelu_erf(v);
+      else if (act == 3) v = tanhf(v);
       C[(size_t)gm * N + gn] = v;
     }
   }
@@ -219,6 +220,160 @@ avgpool_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Bn, 
 cudaError_t launch_avgpool(const float* x, float* y, int Bn, int HW, int C, cudaStream_t s) {
   if (Bn * C <= 0) return cudaSuccess;
   avgpool_nhwc_kernel<<<(Bn * C + 255) / 256, 256, 0, s>>>(x, y, Bn, HW, C);
+  g_launches_nn++;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------- transformer blocks ----
+// block-wide sum of (a, b) with 256 threads
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = make_float2(a, b);
+  __syncthreads();
+  float2 t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : make_float2(0.f, 0.f);
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+      t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+    }
+    if (l == 0) sh[0] = t;
+  }
+  __syncthreads();
+  t = sh[0];
+  __syncthreads();
+  return t;
+}
+
+// one CTA per token: y = LayerNorm(v) * gamma + beta, where v = x[token] (+ res[token]) or, for the embedding
+// op, word[id] + pos[s] + type[0]. Two-pass mean / variance in fp32 (H <= 4096).
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res, const int* __restrict__ ids,
+                 const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int S, int H,
+                 int vocab, float eps) {
+  __shared__ float2 sh[8];
+  extern __shared__ float row[];
+  const int token = blockIdx.x;
+  const float* xr = nullptr;
+  const float* wr = nullptr;
+  if (ids) {
+    int id = __ldg(ids + token);
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    wr = word + (size_t)id * H;
+  } else {
+    xr = x + (size_t)token * H;
+  }
+  float s = 0.f;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float v;
+    if (ids) v = __ldg(wr + h) + __ldg(pos + (size_t)(token % S) * H + h) + __ldg(type + h);
+    else v = __ldg(xr + h) + (res ? __ldg(res + (size_t)token * H + h) : 0.f);
+    row[h] = v;
+    s += v;
+  }
+  const float mean = block_sum2(s, 0.f, sh).x / (float)H;
+  float q = 0.f;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const float d = row[h] - mean;
+    q += d * d;
+  }
+  const float var = block_sum2(q, 0.f, sh).x / (float)H;
+  const float inv = rsqrtf(var + eps);
+  for (int h = threadIdx.x; h < H; h += blockDim.x)
+    y[(size_t)token * H + h] = (row[h] - mean) * inv * __ldg(gamma + h) + __ldg(beta + h);
+}
+
+cudaError_t launch_layernorm(const float* x, const float* res, const int* ids, const float* word, const float* pos,
+                             const float* type, const float* gamma, const float* beta, float* y, int tokens, int S, int H,
+                             int vocab, float eps, cudaStream_t s) {
+  if (tokens <= 0) return cudaSuccess;
+  layernorm_kernel<<<tokens, 256, (size_t)H * sizeof(float), s>>>(x, res, ids, word, pos, type, gamma, beta, y, S, H, vocab, eps);
+  g_launches_nn++;
+  return cudaGetLastError();
+}
+
+// Multi-head self-attention on a packed qkv buffer [B, S, 3H] (q | k | v), one CTA per (batch, head): K and V of
+// the head are staged in shared memory, each warp owns query rows; softmax with warp shuffles; keys whose token
+// id is 0 ([PAD]) get the BERT additive mask -10000. ctx[B, S, H].
+__global__ void __launch_bounds__(256)
+attention_kernel(const float* __restrict__ qkv, const int* __restrict__ ids, float* __restrict__ ctx, int S, int H, int heads) {
+  extern __shared__ float sm[];
+  const int d = H / heads;            // 64 for BERT-base
+  const int b = blockIdx.x / heads, hd = blockIdx.x % heads;
+  float* Ks = sm;                     // [S][d+1]
+  float* Vs = Ks + (size_t)S * (d + 1);  // [S][d]
+  float* Ps = Vs + (size_t)S * d;     // [8 warps][S]
+  float* Qs = Ps + (size_t)8 * S;     // [8 warps][d]
+  float* Ms = Qs + 8 * d;             // [S] additive mask
+  const float* base = qkv + (size_t)b * S * 3 * H;
+  for (int idx = threadIdx.x; idx < S * d; idx += blockDim.x) {
+    const int j = idx / d, c = idx - j * d;
+    Ks[j * (d + 1) + c] = __ldg(base + (size_t)j * 3 * H + H + hd * d + c);
+    Vs[j * d + c] = __ldg(base + (size_t)j * 3 * H + 2 * H + hd * d + c);
+  }
+  for (int j = threadIdx.x; j < S; j += blockDim.x) Ms[j] = (ids && __ldg(ids + (size_t)b * S + j) == 0) ? -10000.f : 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float scale = rsqrtf((float)d);
+  float* P = Ps + warp * S;
+  float* Q = Qs + warp * d;
+  for (int i = warp; i < S; i += 8) {
+    for (int c = lane; c < d; c += 32) Q[c] = __ldg(base + (size_t)i * 3 * H + hd * d + c);
+    __syncwarp();
+    float mx = -FLT_MAX;
+    for (int j = lane; j < S; j += 32) {
+      float sc = 0.f;
+      const float* kr = Ks + j * (d + 1);
+      for (int c = 0; c < d; ++c) sc = fmaf(Q[c], kr[c], sc);
+      sc = sc * scale + Ms[j];
+      P[j] = sc;
+      mx = fmaxf(mx, sc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      const float e = expf(P[j] - mx);
+      P[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    for (int c = lane; c < d; c += 32) {
+      float o = 0.f;
+      for (int j = 0; j < S; ++j) o = fmaf(P[j], Vs[j * d + c], o);
+      ctx[((size_t)b * S + i) * H + hd * d + c] = o * inv;
+    }
+    __syncwarp();
+  }
+}
+
+size_t attention_smem_bytes(int S, int H, int heads) {
+  const int d = H / heads;
+  return ((size_t)S * (d + 1) + (size_t)S * d + (size_t)8 * S + 8 * d + S) * sizeof(float);
+}
+
+cudaError_t launch_attention(const float* qkv, const int* ids, float* ctx, int Bn, int S, int H, int heads, cudaStream_t s) {
+  if (Bn <= 0) return cudaSuccess;
+  const size_t smem = attention_smem_bytes(S, H, heads);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static bool attr[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr[dev & 63] = true;
+  }
+  attention_kernel<<<Bn * heads, 256, smem, s>>>(qkv, ids, ctx, S, H, heads);
   g_launches_nn++;
   return cudaGetLastError();
 }

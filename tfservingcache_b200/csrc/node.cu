@@ -475,7 +475,7 @@ cudaError_t Node::run_model(const DeviceModel& dm, const char* x, int64_t rows, 
         const int K = o.kh * o.kw * o.c;
         const bool direct = o.kh == 1 && o.kw == 1 && o.stride == 1 && o.pad == 0;
         const float* A = src;
-        int lda = K;
+        int lda = o.kind == OpKind::Dense ? (int)o.lda : K;  // Dense over a [S,H] source reads token 0 of every sequence
         if (!direct) {
           lda = (K + 3) / 4 * 4;
           e = launch_im2col(src, (float*)col, B, o.h, o.w, o.c, o.kh, o.kw, o.stride, o.pad, o.oh, o.ow, lda, st);
@@ -485,6 +485,15 @@ cudaError_t Node::run_model(const DeviceModel& dm, const char* x, int64_t rows, 
         e = launch_gemm(A, W, bias, res, dst, B * o.oh * o.ow, o.cout, K, lda, o.act, st);
       } else if (o.kind == OpKind::MaxPool) {
         e = launch_maxpool(src, dst, B, o.h, o.w, o.c, o.kh, o.kw, o.stride, o.pad, o.oh, o.ow, st);
+      } else if (o.kind == OpKind::Embed) {
+        e = launch_layernorm(nullptr, nullptr, (const int*)x, (const float*)(dm.dptr + o.word_off), (const float*)(dm.dptr + o.pos_off),
+                             (const float*)(dm.dptr + o.type_off), (const float*)(dm.dptr + o.w_off), (const float*)(dm.dptr + o.b_off),
+                             dst, B * o.h, o.h, o.c, o.vocab, o.eps, st);
+      } else if (o.kind == OpKind::LayerNorm) {
+        e = launch_layernorm(src, o.res == -100 ? nullptr : (const float*)buf(o.res), nullptr, nullptr, nullptr, nullptr,
+                             (const float*)(dm.dptr + o.w_off), (const float*)(dm.dptr + o.b_off), dst, B * o.h, o.h, o.c, 0, o.eps, st);
+      } else if (o.kind == OpKind::Attention) {
+        e = launch_attention(src, d.input_dtype == TFSC_DT_INT32 ? (const int*)x : nullptr, dst, B, o.h, o.cout, o.heads, st);
       } else {
         e = launch_avgpool(src, dst, B, o.h * o.w, o.c, st);
       }
@@ -558,8 +567,8 @@ int Node::describe(const ModelId& id, ModelDesc* desc, int* outcome, std::string
   return 0;
 }
 
-int Node::predict_host(const ModelId& id, const void* x, int64_t n_elems, const OutAllocFn& y_alloc, int* outcome,
-                       ModelDesc* desc_out, std::string* err) {
+int Node::predict_host(const ModelId& id, const void* x, int64_t n_elems, int in_dtype, const OutAllocFn& y_alloc,
+                       int* outcome, ModelDesc* desc_out, std::string* err) {
   PredictRequest req;
   int rc = fetch(id, &req.dm, err);  // handleModelRequest -> fetchModel, before any input validation (as the reference)
   if (rc < 0) return rc;
@@ -567,6 +576,12 @@ int Node::predict_host(const ModelId& id, const void* x, int64_t n_elems, const 
   const ModelDesc& d = req.dm->desc;
   if (desc_out) *desc_out = d;
   const int64_t per_row = d.tmpl == Template::Affine ? 1 : d.in_dim;
+  if (in_dtype != d.input_dtype) {
+    unpin(req.dm);
+    *err = "input dtype " + std::to_string(in_dtype) + " does not match the model signature (expects dtype " +
+           std::to_string(d.input_dtype) + ")";
+    return TFSC_E_INVALID;
+  }
   if (!x || n_elems <= 0 || n_elems % per_row != 0) {
     unpin(req.dm);
     *err = "input has " + std::to_string(n_elems) + " elements; model " + id.name + " expects a multiple of " +

@@ -79,7 +79,7 @@ class Node {
   // rows are derived from the model (n_elems / in_dim). y_alloc(desc, rows) supplies the output
   // buffer once the model is known (return nullptr to reject, e.g. caller buffer too small).
   using OutAllocFn = std::function<void*(const ModelDesc&, int64_t rows)>;
-  int predict_host(const ModelId& id, const void* x, int64_t n_elems, const OutAllocFn& y_alloc, int* outcome,
+  int predict_host(const ModelId& id, const void* x, int64_t n_elems, int in_dtype, const OutAllocFn& y_alloc, int* outcome,
                    ModelDesc* desc_out, std::string* err);
   // describe a model (triggers fetch): needed to size outputs before predict
   int describe(const ModelId& id, ModelDesc* desc, int* outcome, std::string* err);

@@ -240,10 +240,22 @@ std::shared_ptr<HostModel> SyntheticModelProvider::load_model(const std::string&
     memset(m->data, 0, m->bytes);
     for (size_t i = 0; i < desc_.ops.size(); ++i) {
       const GraphOp& o = desc_.ops[i];
-      if (o.kind != OpKind::Conv && o.kind != OpKind::Dense) continue;
-      const uint64_t fan_in = (uint64_t)o.kh * o.kw * o.c;
-      fill(base + o.w_off / 4, seed, (uint32_t)(2 * i), fan_in * o.cout, (float)std::sqrt(3.0 / (double)fan_in), threads_);
-      fill(base + o.b_off / 4, seed, (uint32_t)(2 * i + 1), (uint64_t)o.cout, 0.1f, 1);
+      const uint32_t t0 = (uint32_t)(8 * i);  // tensor ids of op i: 8*i + {0 kernel/gamma, 1 bias/beta, 2 word, 3 pos, 4 type}
+      if (o.kind == OpKind::Conv || o.kind == OpKind::Dense) {
+        const uint64_t fan_in = (uint64_t)o.kh * o.kw * o.c;
+        fill(base + o.w_off / 4, seed, t0, fan_in * o.cout, (float)std::sqrt(3.0 / (double)fan_in), threads_);
+        fill(base + o.b_off / 4, seed, t0 + 1, (uint64_t)o.cout, 0.1f, 1);
+      } else if (o.kind == OpKind::LayerNorm || o.kind == OpKind::Embed) {
+        float* g = base + o.w_off / 4;
+        fill(g, seed, t0, (uint64_t)o.c, 0.1f, 1);
+        for (int c = 0; c < o.c; ++c) g[c] += 1.0f;  // gamma = 1 + 0.1 u
+        fill(base + o.b_off / 4, seed, t0 + 1, (uint64_t)o.c, 0.1f, 1);
+        if (o.kind == OpKind::Embed) {
+          fill(base + o.word_off / 4, seed, t0 + 2, (uint64_t)o.vocab * o.c, 0.05f, threads_);
+          fill(base + o.pos_off / 4, seed, t0 + 3, (uint64_t)o.max_pos * o.c, 0.05f, 1);
+          fill(base + o.type_off / 4, seed, t0 + 4, (uint64_t)2 * o.c, 0.05f, 1);
+        }
+      }
     }
     return m;
   }

@@ -269,7 +269,8 @@ int tfsc_predict(tfsc_server* s, const char* model_name, const char* version, co
   int rc = resolve(s, model_name, version, &node, &id);
   if (rc < 0) return rc;
   const tfsc_tensor& x = in[0];
-  if (x.dtype != TFSC_DT_FLOAT || x.rank < 0 || x.rank > 8) return fail(TFSC_E_INVALID, "predict: input must be DT_FLOAT, rank <= 8");
+  if ((x.dtype != TFSC_DT_FLOAT && x.dtype != TFSC_DT_INT32) || x.rank < 0 || x.rank > 8)
+    return fail(TFSC_E_INVALID, "predict: input must be DT_FLOAT or DT_INT32, rank <= 8");
   int64_t n = 1;
   std::vector<int64_t> ishape(x.shape, x.shape + x.rank);
   for (auto d : ishape) n *= d;
@@ -292,7 +293,7 @@ int tfsc_predict(tfsc_server* s, const char* model_name, const char* version, co
     o->nbytes = (size_t)on * 4;
     return o->data;
   };
-  rc = node->predict_host(id, x.data, n, alloc, nullptr, nullptr, &err);
+  rc = node->predict_host(id, x.data, n, x.dtype, alloc, nullptr, nullptr, &err);
   if (rc < 0) return fail(rc, "%s", err.c_str());
   return 0;
 }
@@ -323,10 +324,20 @@ int tfsc_grpc_predict(tfsc_server* s, const void* req, size_t req_len, void** re
     return fail(TFSC_E_INVALID, "PredictRequest has no inputs");
   }
   const TensorView& tv = view.inputs[0];
-  const float* xdata = nullptr;
+  const void* xdata = nullptr;
   int64_t n = 0;
   std::vector<float> scratch;
-  bool input_ok = tensor_f32(tv, &xdata, &n, &scratch, &err);
+  std::vector<int32_t> iscratch;
+  bool input_ok;
+  if (tv.dtype == TFSC_DT_INT32) {  // token-id inputs (BERT bundles)
+    const int32_t* ip = nullptr;
+    input_ok = tensor_i32(tv, &ip, &n, &iscratch, &err);
+    xdata = ip;
+  } else {
+    const float* fp = nullptr;
+    input_ok = tensor_f32(tv, &fp, &n, &scratch, &err);
+    xdata = fp;
+  }
   char* buf = nullptr;
   size_t total = 0;
   std::string bad_sig;
@@ -356,7 +367,7 @@ int tfsc_grpc_predict(tfsc_server* s, const void* req, size_t req_len, void** re
     if (rc < 0) return fail(rc, "%s", e2.c_str());
     return fail(TFSC_E_INVALID, "%s", err.c_str());
   }
-  rc = node->predict_host(id, xdata, n, alloc, nullptr, nullptr, &err);
+  rc = node->predict_host(id, xdata, n, tv.dtype == TFSC_DT_INT32 ? TFSC_DT_INT32 : TFSC_DT_FLOAT, alloc, nullptr, nullptr, &err);
   if (rc < 0) {
     free(buf);
     s->fail_grpc++;
@@ -546,7 +557,14 @@ int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const 
       y.resize((size_t)on);
       return y.data();
     };
-    rc = node->predict_host(id, flat.data(), (int64_t)flat.size(), alloc, nullptr, nullptr, &err);
+    rc = node->predict_host(id, flat.data(), (int64_t)flat.size(), TFSC_DT_FLOAT, alloc, nullptr, nullptr, &err);
+    if (rc == TFSC_E_INVALID && err.find("input dtype") == 0) {
+      // JSON numbers carry no dtype: the signature wants int32 (token ids) -> resend the same values as integers
+      std::vector<int32_t> ints(flat.size());
+      for (size_t i = 0; i < flat.size(); ++i) ints[i] = (int32_t)llround((double)flat[i]);
+      err.clear();
+      rc = node->predict_host(id, ints.data(), (int64_t)ints.size(), TFSC_DT_INT32, alloc, nullptr, nullptr, &err);
+    }
     if (rc < 0) return fail_http(bad_sig.empty() ? http_for(rc) : 400, bad_sig.empty() ? err : bad_sig);
     // TF-Serving's writer: 4-space indent, arrays on one line, closing bracket on its own line
     std::string b = std::string("{\n    \"") + (instances ? "predictions" : "outputs") + "\": ";

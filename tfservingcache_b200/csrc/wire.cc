@@ -89,6 +89,17 @@ static bool decode_tensor(const uint8_t* d, size_t n, TensorView* t) {
           t->loose_f32.push_back(fv);
         }
         break;
+      case 7:  // int_val: packed varints (wt 2) or one varint per entry (wt 0)
+        if (wt == 0) t->ints.push_back((int32_t)(int64_t)v);
+        else if (wt == 2) {
+          PbReader r2(p, l);
+          uint64_t vv;
+          while (!r2.done()) {
+            if (!r2.varint(&vv)) return false;
+            t->ints.push_back((int32_t)(int64_t)vv);
+          }
+        }
+        break;
       default: break;  // other typed value fields are rejected later by dtype
     }
   }
@@ -194,6 +205,37 @@ bool tensor_f32(const TensorView& t, const float** data, int64_t* n, std::vector
   }
   *err = "float_val count " + std::to_string(have) + " does not match tensor_shape (" + std::to_string(want) + ")";
   return false;
+}
+
+bool tensor_i32(const TensorView& t, const int32_t** data, int64_t* n, std::vector<int32_t>* scratch, std::string* err) {
+  if (t.dtype != TFSC_DT_INT32) {
+    *err = "input '" + t.name + "' has dtype " + std::to_string(t.dtype) + "; expected DT_INT32 (3)";
+    return false;
+  }
+  for (auto d : t.shape)
+    if (d < 0) {
+      *err = "input '" + t.name + "' has an unknown dimension";
+      return false;
+    }
+  const int64_t want = t.num_elements();
+  if (t.content_len) {
+    if ((int64_t)(t.content_len / 4) != want || t.content_len % 4) {
+      *err = "tensor_content size does not match tensor_shape";
+      return false;
+    }
+    scratch->resize(want);
+    memcpy(scratch->data(), t.content, t.content_len);
+  } else if ((int64_t)t.ints.size() == want) {
+    *scratch = t.ints;
+  } else if (t.ints.size() == 1 && want > 1) {
+    scratch->assign(want, t.ints[0]);
+  } else {
+    *err = "int_val count " + std::to_string(t.ints.size()) + " does not match tensor_shape (" + std::to_string(want) + ")";
+    return false;
+  }
+  *data = scratch->data();
+  *n = want;
+  return true;
 }
 
 void predict_response_frame(const std::string& model_name, int64_t version, const std::string& signature_name,

@@ -19,7 +19,8 @@ struct TensorView {
   size_t content_len = 0;
   const uint8_t* packed_f32 = nullptr;  // packed float_val (field 5, wire type 2)
   size_t packed_f32_len = 0;
-  std::vector<float> loose_f32;  // unpacked float_val entries / double_val / int_val converted
+  std::vector<float> loose_f32;  // unpacked float_val entries
+  std::vector<int32_t> ints;     // int_val entries (packed or not), field 7
   int64_t num_elements() const {
     int64_t n = 1;
     for (auto d : shape) n *= d;
@@ -39,6 +40,9 @@ bool decode_predict_request(const void* data, size_t len, PredictRequestView* ou
 // fp32 elements of a DT_FLOAT tensor; `scratch` is used when the data is not contiguous in the
 // request (unpacked float_val, scalar broadcast).
 bool tensor_f32(const TensorView& t, const float** data, int64_t* n, std::vector<float>* scratch, std::string* err);
+
+// int32 elements of a DT_INT32 tensor (tensor_content or int_val)
+bool tensor_i32(const TensorView& t, const int32_t** data, int64_t* n, std::vector<int32_t>* scratch, std::string* err);
 
 // Serialized PredictResponse{outputs{name: TensorProto{DT_FLOAT, shape, float_val}}, model_spec}
 // split around the float payload: prefix | n_floats*4 payload bytes | suffix.

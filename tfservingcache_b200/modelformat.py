@@ -53,16 +53,28 @@ def _write(version_dir: str, man: dict, blob: np.ndarray):
     blob.astype("<f4").tofile(os.path.join(version_dir, "weights.bin"))
 
 
-def _graph_manifest(input_shape, ops, n_buffers, input_name="x", output_name="y"):
+def _graph_manifest(input_shape, ops, n_buffers, input_name="x", output_name="y", input_dtype="float32"):
     off = 0
+
+    def take(nbytes):
+        nonlocal off
+        o = off
+        off = _align256(off + nbytes)
+        return o
+
     for op in ops:
         if op["op"] in ("conv", "dense"):
             k = op.get("kh", 1) * op.get("kw", 1) * op["c"]
-            op["w_offset"] = off
-            off = _align256(off + k * op["cout"] * 4)
-            op["b_offset"] = off
-            off = _align256(off + op["cout"] * 4)
-    return {"format": "tfsc-b200-v1", "template": "graph", "dtype": "float32",
+            op["w_offset"] = take(k * op["cout"] * 4)
+            op["b_offset"] = take(op["cout"] * 4)
+        elif op["op"] in ("layernorm", "embed"):
+            op["w_offset"] = take(op["c"] * 4)      # gamma
+            op["b_offset"] = take(op["c"] * 4)      # beta
+            if op["op"] == "embed":
+                op["word_offset"] = take(op["vocab"] * op["c"] * 4)
+                op["pos_offset"] = take(op["max_pos"] * op["c"] * 4)
+                op["type_offset"] = take(2 * op["c"] * 4)
+    return {"format": "tfsc-b200-v1", "template": "graph", "dtype": "float32", "input_dtype": input_dtype,
             "signature": {"input": input_name, "output": output_name}, "input_shape": list(input_shape),
             "n_buffers": n_buffers, "ops": ops, "weights_bytes": off}
 
@@ -104,3 +116,30 @@ def resnet50_manifest(image=224, classes=1000, width=64, blocks=(3, 4, 6, 3)):
 
 def write_graph_bundle(version_dir: str, manifest: dict, blob: np.ndarray):
     _write(version_dir, manifest, np.asarray(blob, np.float32))
+
+
+def bert_manifest(seq=128, hidden=768, layers=12, heads=12, inter=3072, vocab=30522, max_pos=512, labels=2):
+    """BERT-base fine-tune variant (Devlin et al. 2018) as a graph bundle: token ids int32 [B, seq] -> logits
+    [B, labels]. A sequence is an "image" with h = seq tokens, w = 1, c = width; dense layers are 1x1 convs; the
+    attention mask is derived from the ids ([PAD] = 0), token_type is 0.
+    Buffers: 0 hidden, 1 qkv / ffn-intermediate, 2 context / post-attention, 3 dense output."""
+    ops = [{"op": "embed", "src": -1, "dst": 0, "h": seq, "w": 1, "c": hidden, "vocab": vocab, "max_pos": max_pos, "eps": 1e-12}]
+
+    def dense(src, dst, cin, cout, act="none", res=None):
+        o = {"op": "conv", "src": src, "dst": dst, "h": seq, "w": 1, "c": cin, "kh": 1, "kw": 1, "stride": 1, "pad": 0,
+             "cout": cout, "act": act}
+        if res is not None:
+            o["res"] = res
+        return o
+
+    for _ in range(layers):
+        ops.append(dense(0, 1, hidden, 3 * hidden))                                     # fused Q|K|V projection
+        ops.append({"op": "attention", "src": 1, "dst": 2, "h": seq, "w": 1, "c": 3 * hidden, "heads": heads})
+        ops.append(dense(2, 3, hidden, hidden))                                         # attention output projection
+        ops.append({"op": "layernorm", "src": 3, "res": 0, "dst": 2, "h": seq, "w": 1, "c": hidden, "eps": 1e-12})
+        ops.append(dense(2, 1, hidden, inter, act="gelu"))
+        ops.append(dense(1, 3, inter, hidden))
+        ops.append({"op": "layernorm", "src": 3, "res": 2, "dst": 0, "h": seq, "w": 1, "c": hidden, "eps": 1e-12})
+    ops.append({"op": "dense", "src": 0, "dst": 1, "h": 1, "w": 1, "c": hidden, "cout": hidden, "act": "tanh"})   # pooler on [CLS]
+    ops.append({"op": "dense", "src": 1, "dst": -2, "h": 1, "w": 1, "c": hidden, "cout": labels, "act": "none"})
+    return _graph_manifest([seq], ops, 4, input_name="input_ids", output_name="logits", input_dtype="int32")

@@ -67,10 +67,11 @@ class Server:
 
     def predict(self, model_name: str, version: str, x: np.ndarray, out_capacity_elems: int | None = None,
                 input_name: str | None = None) -> np.ndarray:
-        x = np.ascontiguousarray(x, dtype=np.float32)
+        is_int = np.issubdtype(np.asarray(x).dtype, np.integer)   # token-id inputs (BERT bundles) travel as DT_INT32
+        x = np.ascontiguousarray(x, dtype=np.int32 if is_int else np.float32)
         tin = TfscTensor()
         tin.name = input_name.encode() if input_name else None
-        tin.dtype = _lib.DT_FLOAT
+        tin.dtype = _lib.DT_INT32 if is_int else _lib.DT_FLOAT
         tin.rank = x.ndim
         for i, d in enumerate(x.shape):
             tin.shape[i] = d
