@@ -154,7 +154,7 @@ __host__ __device__ constexpr uint32_t make_idesc_ts(int n) {
 // TMEM (512 columns): D tile t at columns [t*2RP, (t+1)*2RP): [0,RP) = W_hi.x_hi (main accumulator),
 // [RP,2RP) = W_hi.x_lo + W_lo.x_hi (small terms kept apart from the big one: the tensor core's fp32
 // accumulation truncates, so small terms must not be added into the large running sum);
-// W_lo operand buffers at columns [256 + cb*64 + t*32, +32), cb = k-block parity.
+// A-operand buffers (W_hi raw bits | W_lo) at columns [256 + cb*128 + t*64, +64), cb = k-block parity.
 template <int RP>
 struct TcSmem {
   static constexpr int NS = 6;
@@ -162,7 +162,7 @@ struct TcSmem {
   static constexpr int W_TOTAL = NS * tc::W_BYTES;
   static constexpr int TOTAL = W_TOTAL + 2 * B_BYTES + 256 + 1024;
 };
-constexpr uint32_t kAloCol = 256;
+constexpr uint32_t kAopCol = 256;  // A-operand staging: [cb][tile][hi 32 | lo 32] columns
 
 template <int RP>
 __global__ void __launch_bounds__(tc::THREADS, 1)
@@ -193,7 +193,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap wmap, const float* __restric
     if (lane == 0) {
       for (int s = 0; s < NS; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&empty[s], 1);
+        mbar_init(&empty[s], tc::NUM_CONV_WARPS);  // the converters are the only readers of a W stage
       }
       for (int c = 0; c < 2; ++c) {
         mbar_init(&cfull[c], tc::NUM_CONV_WARPS);
@@ -230,32 +230,30 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap wmap, const float* __restric
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc1 = make_idesc(2 * RP);   // W_hi (smem, MN-major) x [x_hi ; x_lo]
-    constexpr uint32_t idesc2 = make_idesc_ts(RP);    // W_lo (TMEM)           x  x_hi
+    constexpr uint32_t idesc1 = make_idesc_ts(2 * RP);  // W_hi (TMEM) x [x_hi ; x_lo]
+    constexpr uint32_t idesc2 = make_idesc_ts(RP);      // W_lo (TMEM) x  x_hi
     for (int kb = 0; kb < n_kblocks; ++kb) {
-      const int s = kb % NS, cb = kb & 1, cit = kb >> 1;
+      const int cb = kb & 1, cit = kb >> 1;
       if (lane == 0) {
-        mbar_wait(&cfull[cb], cit & 1);  // converters waited on full[s] themselves
+        mbar_wait(&cfull[cb], cit & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         TC_TRACE(1, kb);
-        const uint32_t whi = smem_u32(smem + s * tc::W_BYTES);
         const uint32_t bp = smem_u32(bprime + cb * S::B_BYTES);
 #pragma unroll
         for (int t = 0; t < tc::TILES; ++t) {
           const uint32_t d = tmem_base + (uint32_t)(t * 2 * RP);
-          const uint32_t alo = tmem_base + kAloCol + (uint32_t)(cb * 64 + t * 32);
+          const uint32_t ahi = tmem_base + kAopCol + (uint32_t)(cb * 128 + t * 64);
+          const uint32_t alo = ahi + 32;
 #pragma unroll
           for (int k8 = 0; k8 < tc::BK / 8; ++k8) {
-            // A (MN-major tf32, SWIZZLE_128B_BASE32B): atoms of 4 k-rows x 128 B (32 columns); the 4 slabs
-            // of a tile sit LBO = 512 B apart, consecutive 4-row k groups SBO = 4 KB apart
-            const uint64_t a_hi = make_desc(whi + t * 4 * 512 + k8 * 8192, 512, 4096, 1);
-            // B' (K-major, SWIZZLE_128B): 8-row groups at SBO = 1 KB, k advances 32 B inside the swizzle row
+            // both A operands come from TMEM (an MN-major tf32 A operand read from shared memory costs ~185 clk
+            // per MMA on B200; the TMEM path does not). B' (K-major, SWIZZLE_128B): 8-row groups at SBO = 1 KB,
+            // k advances 32 B inside the swizzle row.
             const uint64_t b = make_desc(bp + k8 * 32, 16, 1024, 2);
-            umma_tf32_ss(d, a_hi, b, idesc1, (kb | k8) ? 1u : 0u);
+            umma_tf32_ts(d, ahi + k8 * 8, b, idesc1, (kb | k8) ? 1u : 0u);
             umma_tf32_ts(d + RP, alo + k8 * 8, b, idesc2, 1u);
           }
         }
-        umma_commit(&empty[s]);
         umma_commit(&cempty[cb]);
         TC_TRACE(2, kb);
       }
@@ -317,11 +315,18 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap wmap, const float* __restric
       mbar_wait(&full[s], it & 1);
       if (ct == 0) TC_TRACE(5, kb);
       const uint32_t wst = w_col_base + (uint32_t)(s * tc::W_BYTES);
-      uint32_t lo[32];
+      uint32_t hi[32], lo[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k)
-        lo[k] = __float_as_uint(tf32_lo(lds_f32(wst + (k >> 2) * 4096 + (k & 3) * 128 + ((((lane >> 3) ^ (k & 3))) << 5))));
-      tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + kAloCol + (uint32_t)(cb * 64 + t * 32), lo);
+      for (int k = 0; k < 32; ++k) {
+        const float v = lds_f32(wst + (k >> 2) * 4096 + (k & 3) * 128 + ((((lane >> 3) ^ (k & 3))) << 5));
+        hi[k] = __float_as_uint(v);  // kind::tf32 ignores the low 13 mantissa bits: W_hi = trunc_tf32(W)
+        lo[k] = __float_as_uint(tf32_lo(v));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with the W stage: TMA may refill it
+      const uint32_t aop = tmem_base + ((uint32_t)(q * 32) << 16) + kAopCol + (uint32_t)(cb * 128 + t * 64);
+      tmem_st32(aop, hi);
+      tmem_st32(aop + 32, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // B' writes -> visible to the MMA (async proxy)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
