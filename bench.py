@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident part alone")
     ap.add_argument("--light-clients", type=int, default=16, help="clients per GPU of the light-load latency probe (0 = skip)")
     ap.add_argument("--dims", type=int, nargs="*", default=None, help="override model dims (debug only)")
-    ap.add_argument("--replica-pick", default="hot-spread", choices=["hot-spread", "random", "first"],
+    ap.add_argument("--replica-pick", default="balanced", choices=["balanced", "hot-spread", "random", "first"],
                     help="replica choice among the ring's GetN candidates (reference: random)")
     return ap.parse_args()
 
@@ -69,7 +69,7 @@ def splitmix(i: np.ndarray) -> np.ndarray:
     return z ^ (z >> np.uint64(31))
 
 
-def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42, pick_policy="hot-spread"):
+def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42, pick_policy="balanced"):
     """Global request stream + ring routing, identical on every rank (no communication)."""
     import tfservingcache_b200 as t
     from oracle.zipf import zipf_trace  # trace generator only (test/bench infrastructure)
@@ -88,7 +88,8 @@ def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42, pick_policy="
     # library's deterministic picker, fed the same global request sequence on every rank so all ranks agree
     picker = t.ReplicaPicker(pick_policy, seed, 0.25)
     keys = [t.model_key(f"m{j}", "1") for j in range(n_models)]
-    pick = np.fromiter((picker.pick(keys[m], replicas, n_gpus) for m in trace.tolist()), dtype=np.int64, count=total)
+    own = [[int(v) for v in owners[j]] for j in range(n_models)]
+    pick = np.fromiter((picker.pick_ids(keys[m], own[m], n_gpus) for m in trace.tolist()), dtype=np.int64, count=total)
     dest = owners[trace, pick]
     return dict(n_models=n_models, replicas=replicas, members=members, trace=trace, dest=dest, owners=owners,
                 pick_policy=pick_policy)

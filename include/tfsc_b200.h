@@ -77,12 +77,16 @@ int tfsc_ring_points(const tfsc_ring* r);               /* ring points (<= 20 * 
  * '\n'-separated, clockwise order, into buf. Returns the number of members written. */
 int tfsc_ring_getn(const tfsc_ring* r, const char* key, int n, char* buf, size_t cap);
 /* Replica choice among the GetN candidates: "random" = the reference (taskhandler.go:91), "first" = primary,
- * "hot-spread" = primary unless the key's recent request share exceeds hot_fraction / members (then random).
+ * "hot-spread" = primary unless the key's recent request share exceeds hot_fraction / members (then random),
+ * "balanced" = hot-spread + least-loaded-replica binding (tfsc_picker_pick_ids).
  * Deterministic for a given seed and call sequence. tfsc_picker_pick returns an index in [0, n_replicas). */
 typedef struct tfsc_picker tfsc_picker;
 tfsc_picker* tfsc_picker_new(const char* policy, uint64_t seed, double hot_fraction);
 void tfsc_picker_free(tfsc_picker* p);
 int tfsc_picker_pick(tfsc_picker* p, const char* key, int n_replicas, int members);
+/* same with a stable integer id per candidate; policy "balanced" = hot-spread + sticky power-of-two-choices
+ * (a cold key binds to the candidate that holds the fewest keys) */
+int tfsc_picker_pick_ids(tfsc_picker* p, const char* key, const int* member_ids, int n_replicas, int members);
 /* key = modelName + "##" + version (taskhandler.go:85). Returns strlen. */
 int tfsc_model_key(const char* model_name, const char* version, char* buf, size_t cap);
 

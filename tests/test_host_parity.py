@@ -313,3 +313,27 @@ def test_replica_picker_policies():
     with pytest.raises(ValueError):
         t.ReplicaPicker("nope", 1)
     assert t.ReplicaPicker("hot-spread", 3).pick("k", 1, 8) == 0
+
+
+def test_balanced_picker_evens_out_keys_per_member():
+    """The 20-vnode ring alone spreads 1000 keys over 8 members within about +-16 %; binding each cold key to the
+    less loaded of its two replicas (sticky power-of-two-choices) brings that to a few keys."""
+    import collections
+    c = t.ClusterConnection(2)
+    members = [t.ServingService(f"gpu{i}", 0, 0) for i in range(8)]
+    c.update(members)
+    pk, pk2 = t.ReplicaPicker("balanced", 7, 0.25), t.ReplicaPicker("balanced", 7, 0.25)
+    bound, first = {}, collections.Counter()
+    for j in range(1000):
+        key = t.model_key(f"m{j}", "1")
+        ids = [int(s.host[3:]) for s in c.find_node_for_key(key)]
+        i = pk.pick_ids(key, ids, 8)
+        assert i == pk2.pick_ids(key, ids, 8)            # deterministic
+        bound[key] = ids[i]
+        first[ids[0]] += 1
+    load = collections.Counter(bound.values())
+    assert max(first.values()) - min(first.values()) > 15    # the ring alone is uneven
+    assert max(load.values()) - min(load.values()) <= 4      # balanced binding is not
+    for key, gpu in list(bound.items())[:200]:              # sticky: a bound key keeps its member
+        ids = [int(s.host[3:]) for s in c.find_node_for_key(key)]
+        assert ids[pk.pick_ids(key, ids, 8)] == gpu

@@ -65,6 +65,7 @@ _sig("tfsc_model_key", C.c_int, cp, cp, C.c_char_p, sz)
 _sig("tfsc_picker_new", vp, cp, C.c_uint64, C.c_double)
 _sig("tfsc_picker_free", None, vp)
 _sig("tfsc_picker_pick", C.c_int, vp, cp, C.c_int, C.c_int)
+_sig("tfsc_picker_pick_ids", C.c_int, vp, cp, C.POINTER(C.c_int), C.c_int, C.c_int)
 _sig("tfsc_lru_new", vp, cp, i64)
 _sig("tfsc_lru_free", None, vp)
 _sig("tfsc_lru_put", C.c_int, vp, cp, i64, cp, i64)

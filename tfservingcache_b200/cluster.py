@@ -70,7 +70,7 @@ class ClusterConnection:
 
 class ReplicaPicker:
     """Replica choice among the GetN candidates: "random" (reference, taskhandler.go:91), "first",
-    "hot-spread" (primary unless the key is hot).  Deterministic for a given seed + call sequence."""
+    "hot-spread" (primary unless the key is hot), "balanced" (hot-spread + least-loaded-replica binding).  Deterministic for a given seed + call sequence."""
 
     def __init__(self, policy: str = "random", seed: int = 0, hot_fraction: float = 0.5):
         self._h = lib.tfsc_picker_new(policy.encode(), seed, hot_fraction)
@@ -84,6 +84,11 @@ class ReplicaPicker:
 
     def pick(self, key: str, n_replicas: int, members: int) -> int:
         return check(lib.tfsc_picker_pick(self._h, key.encode(), n_replicas, members), "picker_pick")
+
+    def pick_ids(self, key: str, member_ids, members: int) -> int:
+        """Same with a stable integer id per candidate replica (needed by the "balanced" policy)."""
+        arr = (C.c_int * len(member_ids))(*[int(v) for v in member_ids])
+        return check(lib.tfsc_picker_pick_ids(self._h, key.encode(), arr, len(member_ids), members), "picker_pick_ids")
 
 
 class TaskHandler:

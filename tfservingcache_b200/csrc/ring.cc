@@ -110,12 +110,11 @@ uint64_t ReplicaPicker::next() {  // xorshift64*
   return rng_ * 0x2545F4914F6CDD1Dull;
 }
 
-int ReplicaPicker::pick(const std::string& key, int n_replicas, int members) {
-  if (n_replicas <= 1 || policy_ == "first") return 0;
-  if (policy_ == "random") return (int)(next() % (uint64_t)n_replicas);
-  // hot-spread: sliding-window request share, halved every 64 Ki requests
+bool ReplicaPicker::note_and_is_hot(const std::string& key, int members) {
+  // sliding-window request share, halved every 64 Ki requests
   uint32_t& c = counts_[key];
   ++c;
+  const uint32_t cur = c;
   if (++window_ >= 65536) {
     for (auto it = counts_.begin(); it != counts_.end();) {
       it->second >>= 1;
@@ -124,8 +123,31 @@ int ReplicaPicker::pick(const std::string& key, int n_replicas, int members) {
     }
     window_ >>= 1;
   }
-  const bool hot = window_ >= 256 && (double)c * (double)(members > 0 ? members : 1) > hot_fraction_ * (double)window_;
-  return hot ? (int)(next() % (uint64_t)n_replicas) : 0;
+  return window_ >= 256 && (double)cur * (double)(members > 0 ? members : 1) > hot_fraction_ * (double)window_;
+}
+
+int ReplicaPicker::pick(const std::string& key, int n_replicas, int members) {
+  if (n_replicas <= 1 || policy_ == "first") return 0;
+  if (policy_ == "random") return (int)(next() % (uint64_t)n_replicas);
+  return note_and_is_hot(key, members) ? (int)(next() % (uint64_t)n_replicas) : 0;
+}
+
+int ReplicaPicker::pick_ids(const std::string& key, const int* member_ids, int n_replicas, int members) {
+  if (policy_ != "balanced" || n_replicas <= 1 || !member_ids) return pick(key, n_replicas, members);
+  if (note_and_is_hot(key, members)) return (int)(next() % (uint64_t)n_replicas);
+  auto it = bound_.find(key);
+  if (it != bound_.end()) {
+    for (int i = 0; i < n_replicas; ++i)
+      if (member_ids[i] == it->second) return i;
+    load_[it->second]--;  // the bound member left the candidate set (membership change): rebind
+    bound_.erase(it);
+  }
+  int best = 0;
+  for (int i = 1; i < n_replicas; ++i)
+    if (load_[member_ids[i]] < load_[member_ids[best]]) best = i;
+  bound_[key] = member_ids[best];
+  load_[member_ids[best]]++;
+  return best;
 }
 
 }  // namespace tfsc
@@ -166,7 +188,7 @@ int tfsc_ring_getn(const tfsc_ring* r, const char* key, int n, char* buf, size_t
 }
 tfsc_picker* tfsc_picker_new(const char* policy, uint64_t seed, double hot_fraction) {
   std::string p = policy ? policy : "random";
-  if (p != "random" && p != "first" && p != "hot-spread") {
+  if (p != "random" && p != "first" && p != "hot-spread" && p != "balanced") {
     tfsc::fail(TFSC_E_INVALID, "unknown proxy.replicaPick '%s'", p.c_str());
     return nullptr;
   }
@@ -176,6 +198,10 @@ void tfsc_picker_free(tfsc_picker* p) { delete p; }
 int tfsc_picker_pick(tfsc_picker* p, const char* key, int n_replicas, int members) {
   if (!p || !key || n_replicas < 1) return tfsc::fail(TFSC_E_INVALID, "picker_pick: bad arguments");
   return p->p.pick(key, n_replicas, members);
+}
+int tfsc_picker_pick_ids(tfsc_picker* p, const char* key, const int* member_ids, int n_replicas, int members) {
+  if (!p || !key || n_replicas < 1) return tfsc::fail(TFSC_E_INVALID, "picker_pick_ids: bad arguments");
+  return p->p.pick_ids(key, member_ids, n_replicas, members);
 }
 int tfsc_model_key(const char* model_name, const char* version, char* buf, size_t cap) {
   if (!model_name || !version) return tfsc::fail(TFSC_E_INVALID, "model_key: bad arguments");

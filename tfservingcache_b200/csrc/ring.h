@@ -40,10 +40,15 @@ class Ring {
 //                models (paging a 1 GB model over PCIe costs ~100x serving it) and k copies of the few hot
 //                ones. Deterministic given the seed and the request sequence, so independent processes
 //                that see the same stream agree without communicating.
+//   "balanced"   hot-spread + sticky power-of-two-choices: the first request of a cold key binds it to the
+//                candidate replica that currently holds the fewest keys (the 20-vnode ring alone is +-16 %
+//                uneven in keys per member; every resident model costs one pass over its weights per tick).
 class ReplicaPicker {
  public:
   ReplicaPicker(const std::string& policy, uint64_t seed, double hot_fraction = 0.5);
   int pick(const std::string& key, int n_replicas, int members);
+  // same, with the identity (any stable integer id) of each candidate; needed by "balanced"
+  int pick_ids(const std::string& key, const int* member_ids, int n_replicas, int members);
   const std::string& policy() const { return policy_; }
 
  private:
@@ -51,8 +56,11 @@ class ReplicaPicker {
   std::string policy_;
   uint64_t rng_;
   double hot_fraction_;
+  bool note_and_is_hot(const std::string& key, int members);
   std::map<std::string, uint32_t> counts_;
   uint64_t window_ = 0;
+  std::map<std::string, int> bound_;  // balanced: key -> member id
+  std::map<int, int> load_;           // balanced: member id -> bound keys
 };
 
 }  // namespace tfsc

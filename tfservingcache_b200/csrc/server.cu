@@ -50,9 +50,11 @@ static int route(tfsc_server* s, const std::string& name, const std::string& ver
       nodes->push_back(it == s->member_node.end() ? -1 : it->second);
     }
   }
-  // "Pick random node", taskhandler.go:91 (policy "random"), or the primary / hot-spread variants
+  // "Pick random node", taskhandler.go:91 (policy "random"), or the primary / hot-spread / balanced variants
+  std::vector<int> ids;
+  for (auto& m : members) ids.push_back((int)(crc32_ieee(m.data(), m.size()) & 0x7FFFFFFF));  // stable id per member
   std::lock_guard<std::mutex> lk(s->pick_mu);
-  *picked = s->picker->pick(key, (int)nodes->size(), n_members);
+  *picked = s->picker->pick_ids(key, ids.data(), (int)nodes->size(), n_members);
   return (int)nodes->size();
 }
 
@@ -105,7 +107,7 @@ tfsc_server* tfsc_server_create(const char* config_json) {
   }
   s->replicas = (int)std::max(s->cfg.get_num("proxy.replicasPerModel", 1), 1.0);
   const std::string policy = s->cfg.get_str("proxy.replicaPick", "random");
-  if (policy != "random" && policy != "first" && policy != "hot-spread") {
+  if (policy != "random" && policy != "first" && policy != "hot-spread" && policy != "balanced") {
     fail(TFSC_E_INVALID, "unknown proxy.replicaPick '%s'", policy.c_str());
     return nullptr;
   }
