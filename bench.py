@@ -271,6 +271,7 @@ def run_b200(args):
     barrier()
     ev0.record(stream)
     alg_bytes, n_req, n_dense = 0, 0, 0
+    t_host0 = time.perf_counter()
     for s in range(W, W + K):
         groups = device_step(s)
         b, l = algorithmic_bytes(groups, dims)
@@ -278,8 +279,10 @@ def run_b200(args):
         n_dense += l
         n_req += sum(r for _m, r in groups)
     ev1.record(stream)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
+    my_elapsed_ms, my_req = elapsed_ms, n_req
     clocks = sampler.stop()
     launches = _lib.lib.tfsc_kernel_launches() - launches0
     st1 = srv.stats()
@@ -323,7 +326,13 @@ def run_b200(args):
         n_l, f_l, el_l, lat_l = e2e_run(e0 + W, e0 + W + e2e_steps, True, clients=args.light_clients, limit=args.light_clients * 64)
         light = {"clients_per_gpu": args.light_clients, "requests": int(n_l), "qps_rank0": round(n_l / el_l, 1),
                  "p50_ms": round(float(np.percentile(lat_l, 50)) / 1e3, 3), "p99_ms": round(float(np.percentile(lat_l, 99)) / 1e3, 3)}
+    per_rank = None
     if world > 1:
+        diag = torch.tensor([my_elapsed_ms, host_enqueue_ms, my_req, n_dense], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(diag) for _ in range(world)]
+        dist.all_gather(allr, diag)
+        per_rank = [{"device_ms": round(float(v[0]), 2), "host_enqueue_ms": round(float(v[1]), 2), "requests": int(v[2]),
+                     "launches": int(v[3])} for v in allr]
         tt = torch.tensor([elapsed_ms, el_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed_ms, el_s = float(tt[0]), float(tt[1])
@@ -378,6 +387,8 @@ def run_b200(args):
                          "launches_timed": n_dense, "avg_launch_us": round(elapsed_ms * 1e3 * world / max(1, n_dense), 2),
                          "note": "per-GPU average algorithmic bytes / max-over-ranks device time"},
         }
+        if per_rank:
+            line["per_rank"] = per_rank
         if cpu_base:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
@@ -496,7 +507,13 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_b200(a)
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_b200(a)
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)  # do not leave the other ranks waiting in a collective

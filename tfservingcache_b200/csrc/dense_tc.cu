@@ -4,13 +4,16 @@
 //
 // The weights are the big streamed operand (1 pass over W per launch, HBM-bound up to ~64 rows), so
 // W^T sits on the MMA "M" side: D[n, r] = sum_k W[k][n] x[r][k].
-//   * W tiles arrive by TMA (cp.async.bulk.tensor.3d, SWIZZLE_128B_ATOM_32B) as MN-major UMMA operands: a 3-D
-//     tensor map {32 n, K, N/32} makes one TMA land 8 slabs of [32 k][32 n] = 256 columns x 32 rows.
-//   * tcgen05.mma.kind::tf32 reads the raw fp32 bits (low 13 mantissa bits ignored) as W_hi; converter
-//     warps compute W_lo = W - trunc_tf32(W) into a second smem tile (same layout, elementwise) and
-//     build B' = [x_hi ; x_lo] (K-major, SW128) from x.
+//   * W tiles arrive by TMA (cp.async.bulk.tensor.3d over a 3-D tensor map {32 n, K, N/32}, boxes of 4 rows x
+//     8 slabs = 4 x 1 KB contiguous) into a 6-stage ring: 192 KB of W in flight per SM.
+//   * 8 converter warps move each tile into TMEM as the MMA "A" operand (lane = output column, column = k):
+//     W_hi = the raw fp32 bits (kind::tf32 ignores the low 13 mantissa bits) and W_lo = W - trunc_tf32(W)
+//     (tcgen05.st), and build B' = [x_hi ; x_lo] (K-major, SWIZZLE_128B) in shared memory from x.
+//     (An MN-major tf32 A operand read straight from shared memory -- layout SWIZZLE_128B_BASE32B, the only one
+//     UMMA accepts for it -- was measured at ~185 clk per MMA on B200; the TMEM path costs ~60.)
 //   * per 8-wide k step and 128-column tile: MMA1 D[:, 0:2R] += W_hi . [x_hi;x_lo]^T (N = 2R),
-//     MMA2 D[:, 0:R] += W_lo . x_hi^T (N = R); accumulators live in TMEM; y = D[:, :R] + D[:, R:2R].
+//     MMA2 D[:, R:2R] += W_lo . x_hi^T (N = R); accumulators live in TMEM; y = D[:, :R] + D[:, R:2R]: the large
+//     term and the small correction terms are kept apart because the tensor core's fp32 accumulation truncates.
 //   * split-K over CTAs (one CTA per SM), partials folded by the last CTA of a strip in fixed order
 //     (same deterministic scheme as dense_stream_kernel), bias + ReLU fused there.
 #include <cuda.h>
@@ -79,14 +82,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
@@ -111,11 +106,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)layout_type << 61;
   return d;
 }
-// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, M=128, A MN-major, B K-major
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-}
-
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
@@ -144,7 +134,8 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       "r"(r[31])
       : "memory");
 }
-// idesc for the TMEM-A MMA: A K-major (A from TMEM cannot be transposed), B K-major
+// cute::UMMA::InstrDescriptor for kind::tf32: fp32 accumulate [4,6)=1, A/B format tf32 [7,10)=[10,13)=2, A K-major
+// (an A operand in TMEM cannot be transposed), B K-major, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc_ts(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }

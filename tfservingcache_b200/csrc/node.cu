@@ -112,8 +112,13 @@ void* Node::host_alloc(size_t bytes, std::function<void(void*, size_t)>* release
   if (!p) {
     DeviceGuard g(cfg_.device);
     if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+      // the host cannot pin more memory (shared box): keep the model in pageable memory; page-ins of this
+      // blob then go through the driver's staging buffers (slower, still correct)
       cudaGetLastError();
-      return nullptr;
+      p = malloc(bytes);
+      if (!p) return nullptr;
+      *release = [](void* q, size_t) { free(q); };
+      return p;
     }
   }
   *release = [this](void* q, size_t n) {
