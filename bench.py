@@ -42,7 +42,7 @@ IN_DIM, OUT_DIM = DIMS[0], DIMS[-1]
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tick", type=int, default=1024, help="requests per GPU per step")
@@ -142,12 +142,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.windows = [], None, gpu_index, []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            # all GPUs of the box are sampled (rank 0 only): a multi-GPU run can be slowed by one throttled device
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -155,7 +156,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
+
+    def mark(self, t0, t1):
+        """A timed window (value or e2e region); only samples inside the marked windows are reported."""
+        self.windows.append((t0, t1))
 
     def stop(self):
         if not self.proc:
@@ -163,17 +168,30 @@ class ClockSampler:
         time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        per = {}
+        for row in self.rows:
+            ts, r = row[0], row[1:]
+            if self.windows and not any(a - 0.05 <= ts <= b + 0.05 for a, b in self.windows):
+                continue
             try:
-                sm.append(float(r[1]))
-                mx = max(mx, float(r[2]))
+                g = int(r[0])
+                d = per.setdefault(g, {"sm": [], "pw": [], "reasons": set()})
+                d["sm"].append(float(r[1]))
+                d["pw"].append(float(r[3]))
+                if g == self.idx:
+                    sm.append(float(r[1]))
+                    mx = max(mx, float(r[2]))
                 for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
                     if r[col].lower().startswith("active"):
-                        reasons.add(name)
+                        d["reasons"].add(name)
+                        if g == self.idx:
+                            reasons.add(name)
             except Exception:
                 pass
+        per_gpu = [{"gpu": g, "sm_mhz": float(np.median(d["sm"])), "power_w": round(float(np.median(d["pw"])), 1),
+                    "reasons": sorted(d["reasons"])} for g, d in sorted(per.items())]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "per_gpu": per_gpu}
 
 
 # ------------------------------------------------------------------------------- b200 impl ------
@@ -272,6 +290,7 @@ def run_b200(args):
     ev0.record(stream)
     alg_bytes, n_req, n_dense = 0, 0, 0
     t_host0 = time.perf_counter()
+    t_wall0 = time.time()
     for s in range(W, W + K):
         groups = device_step(s)
         b, l = algorithmic_bytes(groups, dims)
@@ -281,9 +300,9 @@ def run_b200(args):
     ev1.record(stream)
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     barrier()
+    sampler.mark(t_wall0, time.time())
     elapsed_ms = ev0.elapsed_time(ev1)
     my_elapsed_ms, my_req = elapsed_ms, n_req
-    clocks = sampler.stop()
     launches = _lib.lib.tfsc_kernel_launches() - launches0
     st1 = srv.stats()
 
@@ -317,9 +336,12 @@ def run_b200(args):
     if args.skip_e2e:
         n_e2e, failed, el_s, lat = 0, 0, 1.0, np.zeros(1, np.float32)
     else:
+        t_e0 = time.time()
         n_e2e, failed, el_s, lat = e2e_run(e0 + W, e0 + W + e2e_steps, True)
+        sampler.mark(t_e0, time.time())
     torch.cuda.synchronize()
     ste1 = srv.stats()
+    clocks = sampler.stop()
     # light-load latency probe (north_star: cache-hit p50 < 5 ms): same trace, few closed-loop clients
     light = None
     if args.light_clients > 0 and not args.skip_e2e:
