@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident part alone")
     ap.add_argument("--light-clients", type=int, default=16, help="clients per GPU of the light-load latency probe (0 = skip)")
     ap.add_argument("--dims", type=int, nargs="*", default=None, help="override model dims (debug only)")
+    ap.add_argument("--workload", default="mlp", choices=["mlp", "resnet50"],
+                    help="mlp = BASELINE configs[2] shard (default, the headline); resnet50 = configs[1] (100 ResNet-50 per GPU, "
+                         "32 HBM-resident, LRU paging in the loop) -- an extra line, functional CUDA-core conv path")
     ap.add_argument("--replica-pick", default="balanced", choices=["balanced", "hot-spread", "random", "first"],
                     help="replica choice among the ring's GetN candidates (reference: random)")
     return ap.parse_args()
@@ -215,6 +218,15 @@ def run_b200(args):
     dims = args.dims or DIMS
     in_dim, out_dim = dims[0], dims[-1]
     model_bytes = sum(dims[i] * dims[i + 1] * 4 + dims[i + 1] * 4 for i in range(len(dims) - 1))
+    graph_man = None
+    if args.workload == "resnet50":
+        graph_man = t.modelformat.resnet50_manifest()
+        in_dim, out_dim, model_bytes = 224 * 224 * 3, 1000, graph_man["weights_bytes"]
+        if args.models_per_gpu == MODELS_PER_GPU:
+            args.models_per_gpu = 100
+        if args.tick == 1024:
+            args.tick = 256
+        args.clients = min(args.clients, 256)
     W, K = args.warmup, args.steps
     e2e_steps = args.e2e_steps or K
     n_steps_total = W + K + W + e2e_steps
@@ -232,15 +244,19 @@ def run_b200(args):
                 avail_kb = int(line.split()[1])
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
         host_gib = min(len(my_models) * model_bytes / 2**30 * 1.02 + 1, avail_kb / 2**20 * 0.7 / max(local_world, 1))
+    max_conc = 32 if graph_man else (1 << 20)  # configs[1]: "HBM cache holds 32 models"
     cfg = {"modelProvider.type": "synthetic", "modelProvider.synthetic.dims": dims,
            "modelProvider.synthetic.count": wl["n_models"], "modelProvider.synthetic.namePrefix": "m",
            "modelProvider.synthetic.threads": max(4, min(32, (os.cpu_count() or 8) // max(world, 1))),
            "gpu.devices": [local], "gpu.arenaBytes": arena, "gpu.maxBatch": 64, "gpu.maxRequestRows": 4096,
-           "gpu.stagingSlots": 4, "modelCache.size": int(host_gib * 2**30), "serving.maxConcurrentModels": 1 << 20,
+           "gpu.stagingSlots": 4, "modelCache.size": int(host_gib * 2**30), "serving.maxConcurrentModels": max_conc,
            # routing is done above with the library's ring + picker over the GLOBAL member list; this rank's
            # server only ever sees the requests it owns, so its own ring has a single member
            "proxy.replicasPerModel": 1, "gpu.members": [wl["members"][rank]], "gpu.localMembers": [wl["members"][rank]],
            "proxy.seed": 1, "proxy.replicaPick": "first"}
+    if graph_man:
+        cfg.update({"modelProvider.synthetic.template": "manifest", "modelProvider.synthetic.manifest": graph_man,
+                    "gpu.arenaBytes": min(arena, 16 << 30), "gpu.maxBatch": 16, "gpu.maxRequestRows": 256})
     srv = t.Server(cfg)
 
     # page every model this rank owns into HBM once (cold loads are not part of the steady-state metric;
@@ -271,7 +287,7 @@ def run_b200(args):
         _mine, groups = step_groups(wl, rank, step, tick_global)
         off = 0
         for m, rows in groups:
-            rc = srv.ensure(0, f"m{m}", 1)  # route -> ensure-resident (hit unless the LRU paged it out)
+            srv.ensure_async(0, f"m{m}", 1)  # route -> ensure-resident: a hit, or an LRU reload queued on the copy stream
             srv.predict_device(0, f"m{m}", 1, x_dev.data_ptr() + off * in_dim * 4, rows, y_dev.data_ptr() + off * out_dim * 4, sptr)
             off += rows
         return groups
@@ -293,7 +309,10 @@ def run_b200(args):
     t_wall0 = time.time()
     for s in range(W, W + K):
         groups = device_step(s)
-        b, l = algorithmic_bytes(groups, dims)
+        if graph_man:
+            b, l = 0, 76 * len(groups)
+        else:
+            b, l = algorithmic_bytes(groups, dims)
         alg_bytes += b
         n_dense += l
         n_req += sum(r for _m, r in groups)
@@ -377,9 +396,24 @@ def run_b200(args):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
 
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not graph_man:
         cpu_base = cpu_reference(args.cpu_sample, dims, warm=4)
 
+    roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "traffic": traffic, "kernel": "dense_stream_kernel<R> (<=8 rows) + dense_tc_kernel<RP> (9..64 rows, tcgen05 3xTF32): fused xW+b+ReLU, split-K",
+            "peak_source": peak_src, "launches_timed": n_dense, "avg_launch_us": round(elapsed_ms * 1e3 * world / max(1, n_dense), 2),
+            "note": "per-GPU average algorithmic bytes / max-over-ranks device time"}
+    workload = (f"BASELINE configs[2] per-GPU shard: {args.models_per_gpu} per-tenant 3-layer MLP "
+                f"({'x'.join(map(str, dims))} fp32, {model_bytes} B) per GPU, Zipf alpha=1.0, ring replicas={wl['replicas']} "
+                f"(replica pick: {wl['pick_policy']}); at 8 GPUs = configs[2] (1000 models)")
+    if graph_man:
+        tf_peak = json.load(open(peaks_path)).get("bf16_tflops_sustained", 1405.4) if os.path.exists(peaks_path) else 1400.0
+        tfl = 8.2e9 * n_req_all / world / (elapsed_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": round(tfl, 2), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(tfl / tf_peak, 5), "traffic": None,
+                "kernel": "gemm_f32_kernel (im2col + CUDA-core fp32 GEMM; round-1 functional conv path, not on tcgen05 yet)",
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)", "note": "8.2 GFLOP per 224x224 image"}
+        workload = (f"BASELINE configs[1]: {args.models_per_gpu} ResNet-50 (v1.5, 25.5 M params, {model_bytes} B) per GPU, Zipf alpha=1.0, "
+                    f"HBM cache holds {max_conc} models (serving.maxConcurrentModels), host tier holds all, 1 image per request")
     if rank == 0:
         value = n_req_all / (elapsed_ms * 1e-3)
         e2e_val = n_e2e_all / el_s
@@ -387,12 +421,10 @@ def run_b200(args):
             "metric": "predict_qps", "value": round(value, 1), "unit": "req/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(elapsed_ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2] per-GPU shard: {args.models_per_gpu} per-tenant 3-layer MLP "
-                                   f"({'x'.join(map(str, dims))} fp32, {model_bytes} B) per GPU, Zipf alpha=1.0, ring replicas={wl['replicas']} "
-                                   f"(replica pick: {wl['pick_policy']}); "
-                                   f"at 8 GPUs = configs[2] (1000 models)",
+            "config": {"workload": workload,
                        "models_total": wl["n_models"], "tick_requests_per_gpu": args.tick, "max_rows_per_pass": "8 (SIMT) / 64 (tcgen05 3xTF32)",
-                       "l2": "inputs larger than L2 (>=1 GB of weights streamed per model pass); L2 flushed before timing",
+                       "l2": ("L2 flushed before timing; 100 models x 102 MB of weights cycle through per GPU (> L2)" if graph_man else
+                              "inputs larger than L2 (>=1 GB of weights streamed per model pass); L2 flushed before timing"),
                        "arena_gib": round(arena / 2**30, 1), "host_tier_gib": round(host_gib, 1), "cold_load_s": round(load_s, 1)},
             "e2e": {"value": round(e2e_val, 1), "unit": "req/s",
                     "h2d_bytes_per_step": int((ste1["h2d_input_bytes"] - ste0["h2d_input_bytes"] + ste1["h2d_weight_bytes"] - ste0["h2d_weight_bytes"]) / e2e_steps),
@@ -404,10 +436,7 @@ def run_b200(args):
             "hbm_cache_hit_pct": round(100.0 * (st1["cache_hits_total"] - st0["cache_hits_total"]) / max(1, st1["cache_total"] - st0["cache_total"]), 2),
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "kernel": "dense_stream_kernel<R> (<=8 rows) + dense_tc_kernel<RP> (9..64 rows, tcgen05 3xTF32): fused xW+b+ReLU, split-K", "peak_source": peak_src,
-                         "launches_timed": n_dense, "avg_launch_us": round(elapsed_ms * 1e3 * world / max(1, n_dense), 2),
-                         "note": "per-GPU average algorithmic bytes / max-over-ranks device time"},
+            "roofline": roof,
         }
         if per_rank:
             line["per_rank"] = per_rank

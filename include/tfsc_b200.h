@@ -170,6 +170,9 @@ int tfsc_route(tfsc_server* s, const char* model_name, const char* version, int*
 /* fetchModel (cachemanager.go:91-152) on one node: ensure the model is HBM-resident.
  * Returns TFSC_FETCH_* or an error. Blocks only this caller (per-model load lock). */
 int tfsc_model_ensure(tfsc_server* s, int node, const char* model_name, int64_t version);
+/* Same decision and bookkeeping as tfsc_model_ensure, but returns as soon as the page-in is queued on the copy
+ * stream (state LOADING); launches on the model wait for it on-device (event), the host never blocks. */
+int tfsc_model_ensure_async(tfsc_server* s, int node, const char* model_name, int64_t version);
 /* GetModelStatus (servingcontroller.go:114-138): TFSC_STATE_* or TFSC_E_NOT_FOUND. */
 int tfsc_model_status(tfsc_server* s, int node, const char* model_name, int64_t version);
 /* Resident set, MRU first: "name\tversion\tbytes\tstate\n" lines. Returns count. */

@@ -88,6 +88,7 @@ _sig("tfsc_server_set_members", C.c_int, vp, C.POINTER(cp), C.c_int)
 _sig("tfsc_route", C.c_int, vp, cp, cp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int))
 _sig("tfsc_model_ensure", C.c_int, vp, C.c_int, cp, i64)
 _sig("tfsc_model_status", C.c_int, vp, C.c_int, cp, i64)
+_sig("tfsc_model_ensure_async", C.c_int, vp, C.c_int, cp, i64)
 _sig("tfsc_resident_list", C.c_int, vp, C.c_int, C.c_char_p, sz)
 _sig("tfsc_host_list", C.c_int, vp, C.c_int, C.c_char_p, sz)
 _sig("tfsc_predict", C.c_int, vp, cp, cp, C.POINTER(TfscTensor), C.c_int, C.POINTER(TfscTensor), C.c_int)

@@ -196,6 +196,17 @@ int tfsc_model_ensure(tfsc_server* s, int node, const char* model_name, int64_t 
   return rc;
 }
 
+int tfsc_model_ensure_async(tfsc_server* s, int node, const char* model_name, int64_t version) {
+  Node* n = node_at(s, node);
+  if (!n || !model_name) return TFSC_E_INVALID;
+  std::string err;
+  std::shared_ptr<DeviceModel> dm;
+  int rc = n->fetch({model_name, version}, &dm, &err);
+  if (rc < 0) return fail(rc, "%s", err.c_str());
+  n->unpin(dm);
+  return rc;
+}
+
 int tfsc_model_status(tfsc_server* s, int node, const char* model_name, int64_t version) {
   Node* n = node_at(s, node);
   if (!n || !model_name) return TFSC_E_INVALID;

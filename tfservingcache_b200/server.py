@@ -50,6 +50,10 @@ class Server:
     def ensure(self, node: int, model_name: str, version: int) -> int:
         return check(lib.tfsc_model_ensure(self._h, node, model_name.encode(), version), "model_ensure")
 
+    def ensure_async(self, node: int, model_name: str, version: int) -> int:
+        """fetchModel without waiting for the page-in (launches wait for it on-device)."""
+        return check(lib.tfsc_model_ensure_async(self._h, node, model_name.encode(), version), "model_ensure_async")
+
     def status(self, node: int, model_name: str, version: int) -> int:
         return lib.tfsc_model_status(self._h, node, model_name.encode(), version)
 
