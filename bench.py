@@ -225,8 +225,8 @@ def run_b200(args):
         if args.models_per_gpu == MODELS_PER_GPU:
             args.models_per_gpu = 100
         if args.tick == 1024:
-            args.tick = 256
-        args.clients = min(args.clients, 256)
+            args.tick = 24      # distinct models per tick stay below the 32-model HBM cache (a tick is executed as one batch wave)
+        args.clients = min(args.clients, 64)
     W, K = args.warmup, args.steps
     e2e_steps = args.e2e_steps or K
     n_steps_total = W + K + W + e2e_steps
@@ -284,10 +284,16 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     def device_step(step):
-        _mine, groups = step_groups(wl, rank, step, tick_global)
+        mine, groups = step_groups(wl, rank, step, tick_global)
+        if graph_man:
+            # cache under pressure: one fetchModel per REQUEST in arrival order, so the LRU sees real recency
+            # (hit / reload accounting as in cachemanager.go:91-152); page-ins run on the copy stream
+            for m in mine.tolist():
+                srv.ensure_async(0, f"m{m}", 1)
         off = 0
         for m, rows in groups:
-            srv.ensure_async(0, f"m{m}", 1)  # route -> ensure-resident: a hit, or an LRU reload queued on the copy stream
+            if not graph_man:
+                srv.ensure_async(0, f"m{m}", 1)  # route -> ensure-resident (all hits once the shard is resident)
             srv.predict_device(0, f"m{m}", 1, x_dev.data_ptr() + off * in_dim * 4, rows, y_dev.data_ptr() + off * out_dim * 4, sptr)
             off += rows
         return groups
