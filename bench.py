@@ -64,6 +64,24 @@ def parse_args():
     return ap.parse_args()
 
 
+def effective_cpus() -> int:
+    """CPUs this process may actually use: min(os.cpu_count(), sched affinity, cgroup-v2 cpu.max quota). The GPU boxes
+    expose 128 logical CPUs but cap the container at 16 CPUs of quota; running 128 busy threads there only earns
+    CFS throttling."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 # ------------------------------------------------------------------------------- workload ------
 def splitmix(i: np.ndarray) -> np.ndarray:
     z = (i.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15))
@@ -247,7 +265,7 @@ def run_b200(args):
     max_conc = 32 if graph_man else (1 << 20)  # configs[1]: "HBM cache holds 32 models"
     cfg = {"modelProvider.type": "synthetic", "modelProvider.synthetic.dims": dims,
            "modelProvider.synthetic.count": wl["n_models"], "modelProvider.synthetic.namePrefix": "m",
-           "modelProvider.synthetic.threads": max(4, min(32, (os.cpu_count() or 8) // max(world, 1))),
+           "modelProvider.synthetic.threads": max(1, min(32, effective_cpus() // max(int(os.environ.get("LOCAL_WORLD_SIZE", world)), 1))),
            "gpu.devices": [local], "gpu.arenaBytes": arena, "gpu.maxBatch": 64, "gpu.maxRequestRows": 4096,
            "gpu.stagingSlots": 4, "modelCache.size": int(host_gib * 2**30), "serving.maxConcurrentModels": max_conc,
            # routing is done above with the library's ring + picker over the GLOBAL member list; this rank's
@@ -466,7 +484,7 @@ def cpu_reference(n_sample, dims, warm=4, steps=None):
     from oracle.lrucache import Model, ModelIdentifier
     from oracle.zipf import zipf_trace
 
-    cores = min(os.cpu_count() or 1, 256)
+    cores = min(effective_cpus(), 256)
     liborc = C.CDLL(os.path.join(ROOT, "oracle", "liboracle_ref.so"))
     n_models = MODELS_PER_GPU
     trace = zipf_trace(n_models, 4096, 1.0, 42)

@@ -19,7 +19,7 @@ KNOWN_KEYS = [
     "proxy.replicasPerModel", "proxy.grpcTimeout", "proxy.replicaPick", "proxy.seed", "proxy.hotFraction",
     "logging.level", "logging.format", "healthprobe.modelName",
     "gpu.devices", "gpu.arenaBytes", "gpu.maxBatch", "gpu.maxRequestRows", "gpu.stagingSlots",
-    "gpu.members", "gpu.localMembers",
+    "gpu.members", "gpu.localMembers", "gpu.blockingSync",
 ]
 
 

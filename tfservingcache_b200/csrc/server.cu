@@ -105,6 +105,15 @@ tfsc_server* tfsc_server_create(const char* config_json) {
       return nullptr;
     }
   }
+  if (s->cfg.get_int("gpu.blockingSync", 1)) {
+    // a serving process must not burn host cores spin-waiting on the GPU (the box's CPU quota is shared by all
+    // ranks): make cudaEventSynchronize / cudaStreamSynchronize block. Applies to the primary context, i.e. also
+    // to other CUDA users in this process (torch).
+    for (int d : devices) {
+      DeviceGuard g(d);
+      if (cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync) != cudaSuccess) cudaGetLastError();
+    }
+  }
   s->replicas = (int)std::max(s->cfg.get_num("proxy.replicasPerModel", 1), 1.0);
   const std::string policy = s->cfg.get_str("proxy.replicaPick", "random");
   if (policy != "random" && policy != "first" && policy != "hot-spread" && policy != "balanced") {
