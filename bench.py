@@ -215,6 +215,59 @@ class ClockSampler:
                 "samples": len(sm), "per_gpu": per_gpu}
 
 
+class NvmlSampler:
+    """Per-rank sampler of this rank's own GPU through NVML (20 ms period; nvidia-smi needs > 200 ms per query on an
+    8-GPU box). Reports median SM clock, max clock, median power and the throttle reasons seen inside the marked
+    timed windows. Any failure degrades to an empty record -- it must never break the bench."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.windows, self.ok, self._stop = gpu_index, [], [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def start(self):
+        if self.ok:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = int(reasons_fn(self.h)) if reasons_fn else 0
+                self.rows.append((time.time(), sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def stop(self):
+        self._stop = True
+        rows = [r for r in self.rows if any(a <= r[0] <= b for a, b in self.windows)] if self.windows else self.rows
+        if not self.ok or not rows:
+            return None
+        mask = 0
+        for r in rows:
+            mask |= r[3]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_min_mhz": float(min(r[1] for r in rows)),
+                "sm_max_mhz": float(self.max_sm), "power_w": round(float(np.median([r[2] for r in rows])), 1),
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(rows)}
+
+
 # ------------------------------------------------------------------------------- b200 impl ------
 def run_b200(args):
     import torch
@@ -323,6 +376,8 @@ def run_b200(args):
     flush.fill_(1)  # inputs (>= 1 GB of weights per launch) already exceed L2; flush once anyway
     sampler = ClockSampler(local)
     sampler.start()
+    nvml = NvmlSampler(local)   # every rank watches its own GPU
+    nvml.start()
     launches0 = _lib.lib.tfsc_kernel_launches()
     st0 = srv.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -344,6 +399,7 @@ def run_b200(args):
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     barrier()
     sampler.mark(t_wall0, time.time())
+    nvml.mark(t_wall0, time.time())
     elapsed_ms = ev0.elapsed_time(ev1)
     my_elapsed_ms, my_req = elapsed_ms, n_req
     launches = _lib.lib.tfsc_kernel_launches() - launches0
@@ -382,9 +438,16 @@ def run_b200(args):
         t_e0 = time.time()
         n_e2e, failed, el_s, lat = e2e_run(e0 + W, e0 + W + e2e_steps, True)
         sampler.mark(t_e0, time.time())
+        nvml.mark(t_e0, time.time())
     torch.cuda.synchronize()
     ste1 = srv.stats()
     clocks = sampler.stop()
+    my_nvml = nvml.stop()
+    if my_nvml and (clocks.get("sm_mhz") is None or clocks.get("samples", 0) < 3):
+        clocks.update({k: my_nvml[k] for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")})
+        clocks["source"] = "nvml"
+    if my_nvml:
+        clocks["nvml"] = my_nvml
     # light-load latency probe (north_star: cache-hit p50 < 5 ms): same trace, few closed-loop clients
     light = None
     if args.light_clients > 0 and not args.skip_e2e:
@@ -393,11 +456,15 @@ def run_b200(args):
                  "p50_ms": round(float(np.percentile(lat_l, 50)) / 1e3, 3), "p99_ms": round(float(np.percentile(lat_l, 99)) / 1e3, 3)}
     per_rank = None
     if world > 1:
-        diag = torch.tensor([my_elapsed_ms, host_enqueue_ms, my_req, n_dense], device="cuda", dtype=torch.float64)
+        nv = my_nvml or {}
+        rmask = sum(b for b, n in NvmlSampler.REASONS.items() if n in nv.get("reasons", []))
+        diag = torch.tensor([my_elapsed_ms, host_enqueue_ms, my_req, n_dense, nv.get("sm_mhz", -1), nv.get("sm_min_mhz", -1),
+                             nv.get("power_w", -1), rmask], device="cuda", dtype=torch.float64)
         allr = [torch.zeros_like(diag) for _ in range(world)]
         dist.all_gather(allr, diag)
         per_rank = [{"device_ms": round(float(v[0]), 2), "host_enqueue_ms": round(float(v[1]), 2), "requests": int(v[2]),
-                     "launches": int(v[3])} for v in allr]
+                     "launches": int(v[3]), "sm_mhz": float(v[4]), "sm_min_mhz": float(v[5]), "power_w": float(v[6]),
+                     "reasons": sorted(n for b, n in NvmlSampler.REASONS.items() if int(v[7]) & b)} for v in allr]
         tt = torch.tensor([elapsed_ms, el_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed_ms, el_s = float(tt[0]), float(tt[1])
