@@ -1,0 +1,106 @@
+// Robustness harness for the host-side parsers of libtfsc_b200 (no CUDA): compiled with
+// -fsanitize=address,undefined by tests/test_native_fuzz.py and fed random / mutated inputs. A server must survive
+// malformed PredictRequest bytes, URLs, JSON bodies and manifests without reading out of bounds.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../tfservingcache_b200/csrc/json.h"
+#include "../../tfservingcache_b200/csrc/lru.h"
+#include "../../tfservingcache_b200/csrc/model.h"
+#include "../../tfservingcache_b200/csrc/parse.h"
+#include "../../tfservingcache_b200/csrc/ring.h"
+#include "../../tfservingcache_b200/csrc/wire.h"
+
+using namespace tfsc;
+
+static std::mt19937_64 rng(12345);
+static std::string random_bytes(size_t n) {
+  std::string s(n, 0);
+  for (auto& c : s) c = (char)(rng() & 0xFF);
+  return s;
+}
+static std::string mutate(std::string s) {
+  if (s.empty()) return s;
+  int n = 1 + (int)(rng() % 4);
+  for (int i = 0; i < n; ++i) {
+    size_t p = rng() % s.size();
+    switch (rng() % 4) {
+      case 0: s[p] = (char)(rng() & 0xFF); break;
+      case 1: s.erase(p, 1 + rng() % 3); break;
+      case 2: s.insert(p, random_bytes(1 + rng() % 3)); break;
+      default: s.resize(p); break;
+    }
+    if (s.empty()) break;
+  }
+  return s;
+}
+
+// a well-formed PredictRequest built by hand (model_spec{name, version}, inputs{"x": float tensor})
+static std::string good_request() {
+  auto varint = [](std::string* o, uint64_t v) {
+    while (v >= 0x80) { o->push_back((char)(v | 0x80)); v >>= 7; }
+    o->push_back((char)v);
+  };
+  auto ld = [&](std::string* o, int f, const std::string& p) { varint(o, (f << 3) | 2); varint(o, p.size()); o->append(p); };
+  std::string ver; varint(&ver, 8); varint(&ver, 42);
+  std::string spec; ld(&spec, 1, "foobar"); ld(&spec, 2, ver);
+  std::string dim; varint(&dim, 8); varint(&dim, 2);
+  std::string shape; ld(&shape, 2, dim); ld(&shape, 2, dim);
+  std::string tensor; varint(&tensor, 8); varint(&tensor, 1); ld(&tensor, 2, shape); ld(&tensor, 4, std::string(16, '\x01'));
+  std::string entry; ld(&entry, 1, "x"); ld(&entry, 2, tensor);
+  std::string req; ld(&req, 1, spec); ld(&req, 2, entry); ld(&req, 3, "y");
+  return req;
+}
+
+int main(int argc, char** argv) {
+  const int iters = argc > 1 ? atoi(argv[1]) : 20000;
+  const std::string good = good_request();
+  {  // the good request decodes as expected
+    PredictRequestView v; std::string err;
+    if (!decode_predict_request(good.data(), good.size(), &v, &err) || v.model_name != "foobar" || v.version != 42 ||
+        v.inputs.size() != 1 || v.inputs[0].shape.size() != 2 || v.output_filter.size() != 1) { fprintf(stderr, "good request failed\n"); return 1; }
+    const float* d; int64_t n; std::vector<float> sc;
+    if (!tensor_f32(v.inputs[0], &d, &n, &sc, &err) || n != 4) { fprintf(stderr, "good tensor failed\n"); return 1; }
+  }
+  const std::string good_json = "{\"instances\": [[1.0, 2.5e3, -3], [4, 5, 6]], \"signature_name\": \"serving_default\", \"x\": {\"a\": [true, null, \"s\\u00e9\"]}}";
+  const std::string good_manifest = "{\"format\":\"tfsc-b200-v1\",\"template\":\"mlp\",\"dtype\":\"float32\",\"weights_bytes\":1280,\"layers\":[{\"in\":8,\"out\":16,\"activation\":\"relu\",\"w_offset\":0,\"b_offset\":512},{\"in\":16,\"out\":4,\"activation\":\"linear\",\"w_offset\":768,\"b_offset\":1024}]}";
+  long decoded = 0, jsons = 0, manifests = 0;
+  for (int i = 0; i < iters; ++i) {
+    std::string in = (i % 3 == 0) ? random_bytes(rng() % 200) : mutate(good);
+    PredictRequestView v; std::string err;
+    if (decode_predict_request(in.data(), in.size(), &v, &err)) {
+      ++decoded;
+      for (auto& t : v.inputs) {
+        const float* d; int64_t n; std::vector<float> sc;
+        if (tensor_f32(t, &d, &n, &sc, &err)) { volatile float s = 0; for (int64_t k = 0; k < n; ++k) s += d[k]; (void)s; }
+        const int32_t* di; std::vector<int32_t> si;
+        if (tensor_i32(t, &di, &n, &si, &err)) { volatile int s = 0; for (int64_t k = 0; k < n; ++k) s += di[k]; (void)s; }
+      }
+    }
+    std::string name; bool has; int64_t ver;
+    scan_model_spec(in.data(), in.size(), &name, &has, &ver, nullptr);
+    std::string url = (i % 2) ? mutate("/v1/models/foobar/versions/42:predict") : random_bytes(rng() % 60), n2, v2;
+    match_rest_url(url, &n2, &v2);
+    int64_t pv; parse_int64(mutate("9223372036854775807"), &pv);
+    Json j; std::string js = (i % 2) ? mutate(good_json) : random_bytes(rng() % 100);
+    if (json_parse(js, &j, &err)) ++jsons;
+    Json mj; std::string ms = mutate(good_manifest);
+    if (json_parse(ms, &mj, &err)) { ModelDesc d; if (parse_manifest(mj, &d, &err)) ++manifests; }
+  }
+  // ring + LRU under churn
+  Ring ring; std::vector<std::string> members;
+  LRUCache lru("", 1000);
+  for (int i = 0; i < 2000; ++i) {
+    if (rng() % 10 == 0) { members.clear(); int n = rng() % 12; for (int k = 0; k < n; ++k) members.push_back("h" + std::to_string(rng() % 20) + ":1:2"); ring.set(members); }
+    std::vector<std::string> out; ring.get_n("key" + std::to_string(rng() % 100), 1 + rng() % 4, &out);
+    ModelId id{"m" + std::to_string(rng() % 30), (int64_t)(rng() % 3)};
+    if (rng() % 2) lru.put(id, CachedModel{id, "p", (int64_t)(rng() % 400)}); else lru.get(id, nullptr);
+    if (lru.current_size() < 0) { fprintf(stderr, "negative LRU size\n"); return 1; }
+  }
+  printf("fuzz ok: %d iterations, %ld requests decoded, %ld json parsed, %ld manifests accepted\n", iters, decoded, jsons, manifests);
+  return 0;
+}
