@@ -36,7 +36,7 @@ def build_pool():
     from google.protobuf import wrappers_pb2, any_pb2  # noqa: F401  (well-known deps)
     pool = descriptor_pool.Default()
     fds = {}
-    for sub in ("core/framework", "serving"):
+    for sub in ("core/framework", "core/lib/core", "serving"):
         d = os.path.join(REF, sub)
         for fn in sorted(os.listdir(d)):
             if fn.endswith(".pb.go"):
@@ -56,9 +56,11 @@ def build_pool():
             pass
         done.add(name)
 
-    for want in ("tensorflow_serving/apis/predict.proto",):
+    for want in ("tensorflow_serving/apis/predict.proto", "tensorflow_serving/apis/get_model_status.proto",
+                 "tensorflow_serving/apis/model_management.proto"):
         add(want)
     get = lambda full: message_factory.GetMessageClass(pool.FindMessageTypeByName(full))
+    build_pool.get = get
     return get("tensorflow.serving.PredictRequest"), get("tensorflow.serving.PredictResponse")
 
 
@@ -106,6 +108,32 @@ def wire_golden():
             "response": {"name": "half_plus_two", "version": 123, "signature": "serving_default", "key": "y",
                          "shape": [3], "values": [2.5, 3.0, 4.5],
                          "response_b64": base64.b64encode(resp.SerializeToString(deterministic=True)).decode()}}
+
+
+def modelservice_golden():
+    """GetModelStatus / ReloadConfig messages as the reference's TFServingController builds them
+    (servingcontroller.go:88-138,159-187), serialized by python-protobuf from the reference's embedded schema."""
+    build_pool()
+    get = build_pool.get
+    Req, Resp = get("tensorflow.serving.GetModelStatusRequest"), get("tensorflow.serving.GetModelStatusResponse")
+    RReq, RResp = get("tensorflow.serving.ReloadConfigRequest"), get("tensorflow.serving.ReloadConfigResponse")
+    out = {}
+    r = Req(); r.model_spec.name = "foo"; r.model_spec.version.value = 42
+    out["status_request"] = {"name": "foo", "version": 42, "b64": base64.b64encode(r.SerializeToString(deterministic=True)).decode()}
+    r2 = Req(); r2.model_spec.name = "__TFSERVINGCACHE_PROBE_CHECK__"; r2.model_spec.version.value = 1
+    out["probe_request"] = {"name": "__TFSERVINGCACHE_PROBE_CHECK__", "version": 1, "b64": base64.b64encode(r2.SerializeToString(deterministic=True)).decode()}
+    resp = Resp(); m = resp.model_version_status.add(); m.version = 123; m.state = 30; m.status.error_code = 0; m.status.error_message = ""
+    m.status.SetInParent()
+    out["status_response"] = {"statuses": [[123, 30, 0, ""]], "b64": base64.b64encode(resp.SerializeToString(deterministic=True)).decode()}
+    rr = RReq()
+    models = [("a", "/models/a", "tensorflow", [1, 2]), ("b", "/models/b", "tensorflow", [7])]
+    for name, base, plat, vers in models:
+        c = rr.config.model_config_list.config.add(); c.name = name; c.base_path = base; c.model_platform = plat
+        c.model_version_policy.specific.versions.extend(vers)
+    out["reload_request"] = {"models": [[n, b, p, v] for n, b, p, v in models], "b64": base64.b64encode(rr.SerializeToString(deterministic=True)).decode()}
+    ok = RResp(); ok.status.SetInParent()
+    out["reload_response_ok"] = {"b64": base64.b64encode(ok.SerializeToString(deterministic=True)).decode()}
+    return out
 
 
 def ring_golden():
@@ -159,4 +187,5 @@ if __name__ == "__main__":
     json.dump(wire_golden(), open(os.path.join(here, "wire_golden.json"), "w"), indent=1)
     json.dump(ring_golden(), open(os.path.join(here, "ring_golden.json"), "w"), indent=1)
     json.dump(trace_golden(), open(os.path.join(here, "trace_golden.json"), "w"), indent=1)
+    json.dump(modelservice_golden(), open(os.path.join(here, "modelservice_golden.json"), "w"), indent=1)
     print("golden fixtures written")

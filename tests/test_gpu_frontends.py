@@ -100,3 +100,32 @@ def test_metrics_endpoint_keeps_reference_metric_names(endpoints):
                  "tfservingcache_proxy_requests_total", "tfservingcache_proxy_failures_total", "tfservingcache_hbm_cache_hit_ratio"):
         assert f"# TYPE {name} " in text
     assert 'tfservingcache_cache_total{model="all_models",version="-1"}' in text
+
+
+def test_tfserving_facade_model_service(endpoints, golden):
+    """The two ModelService RPCs the reference's TFServingController issues (servingcontroller.go:88-138), so the
+    unmodified reference can point serving.grpcHost at this server."""
+    import base64
+    import grpc
+    from tfservingcache_b200 import tfs_wire
+    srv, _, target = endpoints
+    ch = grpc.insecure_channel(target)
+    raw = dict(request_serializer=lambda b: b, response_deserializer=lambda b: b)
+    status = ch.unary_unary("/tensorflow.serving.ModelService/GetModelStatus", **raw)
+    reload_cfg = ch.unary_unary("/tensorflow.serving.ModelService/HandleReloadConfigRequest", **raw)
+    # health probe of the reference: a model that does not exist must answer NOT_FOUND (code 5), cachemanager.go:76-89
+    probe = base64.b64decode(golden("modelservice_golden.json")["probe_request"]["b64"])
+    with pytest.raises(grpc.RpcError) as e:
+        status(probe)
+    assert e.value.code() == grpc.StatusCode.NOT_FOUND
+    # ReloadConfig as createModelConfig builds it, then poll status like reloadServingConfig does
+    req = tfs_wire.encode_reload_config_request([("m9", "/models/m9", "tensorflow", [1]), ("m10", "/models/m10", "tensorflow", [1])])
+    assert tfs_wire.decode_reload_config_response(reload_cfg(req)) == (0, "")
+    for name in ("m9", "m10"):
+        got = tfs_wire.decode_get_model_status_response(status(tfs_wire.encode_get_model_status_request(name, 1)))
+        assert got == [(1, 30, 0, "")]          # AVAILABLE
+    assert [n for n, *_ in srv.resident(0)][:2] == ["m9", "m10"]   # first listed = most recently used
+    # unknown model in the config -> error status in the response (TF-Serving reports it the same way)
+    code, msg = tfs_wire.decode_reload_config_response(reload_cfg(tfs_wire.encode_reload_config_request([("zzz", "/models/zzz", "tensorflow", [1])])))
+    assert code == 5 and "No matching model" in msg
+    ch.close()

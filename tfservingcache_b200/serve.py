@@ -14,7 +14,7 @@ import threading
 from concurrent import futures
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 
-from . import _lib
+from . import _lib, tfs_wire
 from .config import load_config
 from .server import Server
 
@@ -105,6 +105,52 @@ def make_grpc_server(srv: Server, port: int, max_msg: int = 16 * 1024 * 1024, wo
             context.abort(grpc.StatusCode.UNIMPLEMENTED, f"{name} not supported")
         return fn
 
+    # ---- TF-Serving facade: tensorflow.serving.ModelService, the two RPCs the reference's TFServingController
+    # issues (servingcontroller.go:88-138). With it the UNMODIFIED reference can use this server as its
+    # serving.grpcHost / restHost instead of a tensorflow/serving container.
+    def get_model_status(request: bytes, context):
+        try:
+            name, version = tfs_wire.decode_get_model_status_request(request)
+        except Exception as e:  # malformed request
+            context.abort(grpc.StatusCode.INVALID_ARGUMENT, str(e))
+        found = []
+        for node in range(srv.num_nodes):
+            if version is not None:
+                st = srv.status(node, name, version)
+                if st >= 0:
+                    found.append((version, st, 0, ""))
+            else:
+                known = {v for n, v, _b in srv.host_models(node) if n == name}
+                for v in sorted(known):
+                    st = srv.status(node, name, v)
+                    if st >= 0:
+                        found.append((v, st, 0, ""))
+        if not found:
+            # TF-Serving answers NOT_FOUND; the reference's health probe depends on exactly that code (cachemanager.go:80-84)
+            context.abort(grpc.StatusCode.NOT_FOUND, f"Could not find any versions of model {name}")
+        best = {}
+        for v, st, c, m in found:   # a model spread over several GPUs: report its most advanced replica
+            if v not in best or st == _lib.STATE_AVAILABLE:
+                best[v] = (v, st, c, m)
+        return tfs_wire.encode_get_model_status_response([best[v] for v in sorted(best)])
+
+    def handle_reload_config(request: bytes, context):
+        try:
+            models = tfs_wire.decode_reload_config_request(request)
+        except Exception as e:
+            context.abort(grpc.StatusCode.INVALID_ARGUMENT, str(e))
+        # the reference lists the models to keep loaded MRU-first (cachemanager.go:167-170): touch them in reverse so
+        # the first ends up most recently used; the HBM tier is an LRU, unlisted models simply age out
+        try:
+            for name, _base, _platform, versions in reversed(models):
+                for v in reversed(versions):
+                    nodes, picked = srv.route(name, str(v))
+                    if nodes[picked] >= 0:
+                        srv.ensure(nodes[picked], name, v)
+        except _lib.TfscError as e:
+            return tfs_wire.encode_reload_config_response(-e.code if -17 < e.code < 0 else 13, str(e))
+        return tfs_wire.encode_reload_config_response()
+
     health_status = {"serving": True}
 
     def health_check(request: bytes, context):
@@ -119,6 +165,9 @@ def make_grpc_server(srv: Server, port: int, max_msg: int = 16 * 1024 * 1024, wo
         grpc.method_handlers_generic_handler("tensorflow.serving.PredictionService", methods),
         grpc.method_handlers_generic_handler("tensorflow.serving.SessionService",
                                              {"SessionRun": grpc.unary_unary_rpc_method_handler(unsupported("SessionRun"), ident, ident)}),
+        grpc.method_handlers_generic_handler("tensorflow.serving.ModelService", {
+            "GetModelStatus": grpc.unary_unary_rpc_method_handler(get_model_status, ident, ident),
+            "HandleReloadConfigRequest": grpc.unary_unary_rpc_method_handler(handle_reload_config, ident, ident)}),
         grpc.method_handlers_generic_handler("grpc.health.v1.Health",
                                              {"Check": grpc.unary_unary_rpc_method_handler(health_check, ident, ident)}),
     ))

@@ -1,0 +1,203 @@
+"""Wire codec (hand-rolled protobuf) for the two TF-Serving ModelService RPCs the reference's TFServingController
+issues (pkg/cachemanager/servingcontroller.go:88-138): HandleReloadConfigRequest and GetModelStatus. Field numbers:
+proto/tensorflow/serving/{get_model_status,model_management,model_server_config,file_system_storage_path_source,
+status}.pb.go. Used by serve.py's TF-Serving facade so the UNMODIFIED reference can point serving.grpcHost at this
+server instead of a tensorflow/serving container."""
+from __future__ import annotations
+
+
+def _varint(v: int) -> bytes:
+    v &= (1 << 64) - 1
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _ld(field: int, payload: bytes) -> bytes:
+    return _varint((field << 3) | 2) + _varint(len(payload)) + payload
+
+
+def _vi(field: int, v: int) -> bytes:
+    return _varint(field << 3) + _varint(v)
+
+
+def _fields(buf: bytes):
+    pos, n = 0, len(buf)
+    while pos < n:
+        key = shift = 0
+        while True:
+            b = buf[pos]
+            pos += 1
+            key |= (b & 0x7F) << shift
+            if not b & 0x80:
+                break
+            shift += 7
+        f, wt = key >> 3, key & 7
+        if wt == 0:
+            v = shift = 0
+            while True:
+                b = buf[pos]
+                pos += 1
+                v |= (b & 0x7F) << shift
+                if not b & 0x80:
+                    break
+                shift += 7
+        elif wt == 2:
+            ln = shift = 0
+            while True:
+                b = buf[pos]
+                pos += 1
+                ln |= (b & 0x7F) << shift
+                if not b & 0x80:
+                    break
+                shift += 7
+            if pos + ln > n:
+                raise ValueError("truncated message")
+            v = bytes(buf[pos:pos + ln])
+            pos += ln
+        elif wt == 1:
+            v = bytes(buf[pos:pos + 8])
+            pos += 8
+        elif wt == 5:
+            v = bytes(buf[pos:pos + 4])
+            pos += 4
+        else:
+            raise ValueError(f"unsupported wire type {wt}")
+        yield f, wt, v
+
+
+def _i64(v: int) -> int:
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def decode_get_model_status_request(buf: bytes):
+    """-> (name, version or None)"""
+    name, version = "", None
+    for f, wt, v in _fields(buf):
+        if f == 1 and wt == 2:  # ModelSpec
+            for f2, wt2, v2 in _fields(v):
+                if f2 == 1 and wt2 == 2:
+                    name = v2.decode()
+                elif f2 == 2 and wt2 == 2:
+                    version = 0
+                    for f3, wt3, v3 in _fields(v2):
+                        if f3 == 1 and wt3 == 0:
+                            version = _i64(v3)
+    return name, version
+
+
+def encode_get_model_status_request(name: str, version: int | None) -> bytes:
+    spec = _ld(1, name.encode()) if name else b""
+    if version is not None:
+        spec += _ld(2, _vi(1, version) if version else b"")
+    return _ld(1, spec)
+
+
+def encode_get_model_status_response(statuses) -> bytes:
+    """statuses: [(version, state, error_code, error_message)]"""
+    out = b""
+    for version, state, code, msg in statuses:
+        st = (_vi(1, code) if code else b"") + (_ld(2, msg.encode()) if msg else b"")
+        m = (_vi(1, version) if version else b"") + (_vi(2, state) if state else b"") + _ld(3, st)
+        out += _ld(1, m)
+    return out
+
+
+def decode_get_model_status_response(buf: bytes):
+    out = []
+    for f, wt, v in _fields(buf):
+        if f == 1 and wt == 2:
+            version = state = code = 0
+            msg = ""
+            for f2, wt2, v2 in _fields(v):
+                if f2 == 1 and wt2 == 0:
+                    version = _i64(v2)
+                elif f2 == 2 and wt2 == 0:
+                    state = v2
+                elif f2 == 3 and wt2 == 2:
+                    for f3, wt3, v3 in _fields(v2):
+                        if f3 == 1 and wt3 == 0:
+                            code = v3
+                        elif f3 == 2 and wt3 == 2:
+                            msg = v3.decode()
+            out.append((version, state, code, msg))
+    return out
+
+
+def decode_reload_config_request(buf: bytes):
+    """-> [(name, base_path, model_platform, [versions])] in list order (createModelConfig, servingcontroller.go:159-187)"""
+    models = []
+    for f, wt, v in _fields(buf):
+        if not (f == 1 and wt == 2):      # ReloadConfigRequest.config
+            continue
+        for f2, wt2, v2 in _fields(v):
+            if not (f2 == 1 and wt2 == 2):  # ModelServerConfig.model_config_list
+                continue
+            for f3, wt3, v3 in _fields(v2):
+                if not (f3 == 1 and wt3 == 2):  # ModelConfigList.config
+                    continue
+                name = base = platform = ""
+                versions = []
+                for f4, wt4, v4 in _fields(v3):
+                    if f4 == 1 and wt4 == 2:
+                        name = v4.decode()
+                    elif f4 == 2 and wt4 == 2:
+                        base = v4.decode()
+                    elif f4 == 4 and wt4 == 2:
+                        platform = v4.decode()
+                    elif f4 == 7 and wt4 == 2:   # ServableVersionPolicy
+                        for f5, wt5, v5 in _fields(v4):
+                            if f5 == 102 and wt5 == 2:  # Specific
+                                for f6, wt6, v6 in _fields(v5):
+                                    if f6 == 1 and wt6 == 0:
+                                        versions.append(_i64(v6))
+                                    elif f6 == 1 and wt6 == 2:  # packed
+                                        versions += [_i64(x) for _f, _w, x in _fields(b"".join(b"\x08" + _varint(y) for y in _unpack(v6)))]
+                models.append((name, base, platform, versions))
+    return models
+
+
+def _unpack(buf: bytes):
+    pos, n = 0, len(buf)
+    while pos < n:
+        v = shift = 0
+        while True:
+            b = buf[pos]
+            pos += 1
+            v |= (b & 0x7F) << shift
+            if not b & 0x80:
+                break
+            shift += 7
+        yield v
+
+
+def encode_reload_config_request(models) -> bytes:
+    cfgs = b""
+    for name, base, platform, versions in models:
+        spec = _ld(1, b"".join(_varint(v) for v in versions))
+        m = _ld(1, name.encode()) + _ld(2, base.encode()) + _ld(4, platform.encode()) + _ld(7, _ld(102, spec))
+        cfgs += _ld(1, m)
+    return _ld(1, _ld(1, cfgs))
+
+
+def encode_reload_config_response(code: int = 0, message: str = "") -> bytes:
+    st = (_vi(1, code) if code else b"") + (_ld(2, message.encode()) if message else b"")
+    return _ld(1, st)
+
+
+def decode_reload_config_response(buf: bytes):
+    code, msg = 0, ""
+    for f, wt, v in _fields(buf):
+        if f == 1 and wt == 2:
+            for f2, wt2, v2 in _fields(v):
+                if f2 == 1 and wt2 == 0:
+                    code = v2
+                elif f2 == 2 and wt2 == 2:
+                    msg = v2.decode()
+    return code, msg
