@@ -40,6 +40,12 @@ cudaError_t launch_layernorm(const float* x, const float* res, const int* ids, c
 cudaError_t launch_attention(const float* qkv, const int* ids, float* ctx, int Bn, int S, int H, int heads, cudaStream_t s);
 size_t attention_smem_bytes(int S, int H, int heads);
 
+// tcgen05 3xTF32 version of launch_gemm (gemm_tc.cu) for M >= 64, N % 32 == 0, K >= 32, lda % 4 == 0
+bool gemm_tc_supported(const float* A, const float* B, const float* bias, const float* R, const float* C, int M, int N, int K,
+                       int lda);
+cudaError_t launch_gemm_tc(const float* A, const float* B, const float* bias, const float* R, float* C, int M, int N, int K,
+                           int lda, int act, cudaStream_t s);
+
 int64_t kernel_launch_count();
 
 }  // namespace tfsc

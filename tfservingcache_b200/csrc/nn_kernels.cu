@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <cfloat>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -132,9 +133,19 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, const 
   }
 }
 
+static bool gemm_tc_enabled() {  // TFSC_GEMM_TC=0 forces the CUDA-core GEMM
+  static int v = [] {
+    const char* e = getenv("TFSC_GEMM_TC");
+    return e ? atoi(e) : 0;
+  }();
+  return v != 0;
+}
+
 cudaError_t launch_gemm(const float* A, const float* B, const float* bias, const float* R, float* C, int M, int N, int K,
                         int lda, int act, cudaStream_t s) {
   if (M <= 0 || N <= 0) return cudaSuccess;
+  if (gemm_tc_enabled() && gemm_tc_supported(A, B, bias, R, C, M, N, K, lda))
+    return launch_gemm_tc(A, B, bias, R, C, M, N, K, lda, act, s);
   dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM);
   const bool vec = (lda % 4 == 0) && (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(B) & 15) == 0);

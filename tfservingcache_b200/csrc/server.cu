@@ -707,6 +707,14 @@ int tfsc_k_gemm(const float* a, const float* b, const float* bias, const float* 
   cudaError_t e = launch_gemm(a, b, bias, r, c, m, n, k, lda, act, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "gemm: %s", cudaGetErrorString(e));
 }
+int tfsc_k_gemm_tc(const float* a, const float* b, const float* bias, const float* r, float* c, int m, int n, int k, int lda,
+                   int act, void* stream) {
+  if (int rc = check_device()) return rc;
+  if (!gemm_tc_supported(a, b, bias, r, c, m, n, k, lda))
+    return fail(TFSC_E_INVALID, "gemm_tc: unsupported shape/alignment (m>=64, n>=64, n%%32==0, k>=32, lda%%4==0, 16B-aligned)");
+  cudaError_t e = launch_gemm_tc(a, b, bias, r, c, m, n, k, lda, act, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "gemm_tc: %s", cudaGetErrorString(e));
+}
 int tfsc_k_im2col(const float* x, float* col, int batch, int h, int w, int c, int kh, int kw, int stride, int pad, int ldc,
                   void* stream) {
   if (int rc = check_device()) return rc;
