@@ -43,6 +43,39 @@ def test_k_gemm(m, n, k, lda, act):
     assert _err(cd.cpu().numpy(), ref) <= TOL
 
 
+@pytest.mark.parametrize("m,n,k,lda", [(128, 128, 32, 32), (64, 64, 64, 64), (300, 256, 96, 96), (3136, 64, 147, 148), (1024, 768, 768, 768),
+                                        (1000, 3072, 768, 768), (512, 768, 3072, 3072), (6272, 128, 1152, 1152), (130, 96, 40, 44)])
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_k_gemm_tc_matches_oracle(m, n, k, lda, act):
+    """tcgen05 / TMEM 3xTF32 GEMM (gemm_tc.cu) vs fp64; bias + residual + activation fused in the epilogue."""
+    torch = _torch()
+    rng = np.random.default_rng(m + n + k + act)
+    a = rng.standard_normal((m, lda)).astype(np.float32)
+    b = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32)
+    r = rng.standard_normal((m, n)).astype(np.float32)
+    ad, bd, biasd, rd = (torch.from_numpy(v).cuda() for v in (a, b, bias, r))
+    cd = torch.full((m, n), float("nan"), device="cuda")
+    t._lib.check(lib.tfsc_k_gemm_tc(ad.data_ptr(), bd.data_ptr(), biasd.data_ptr(), rd.data_ptr(), cd.data_ptr(), m, n, k, lda, act, None), "gemm_tc")
+    torch.cuda.synchronize()
+    ref = a[:, :k].astype(np.float64) @ b.astype(np.float64) + bias + r
+    if act == 1:
+        ref = np.maximum(ref, 0)
+    elif act == 2:
+        ref = torch.nn.functional.gelu(torch.from_numpy(ref)).numpy()
+    elif act == 3:
+        ref = np.tanh(ref)
+    got = cd.cpu().numpy()
+    assert not np.isnan(got).any() and _err(got, ref) <= TOL
+
+
+def test_k_gemm_tc_rejects_unsupported_shapes():
+    torch = _torch()
+    x = torch.zeros(64, 64, device="cuda")
+    assert lib.tfsc_k_gemm_tc(x.data_ptr(), x.data_ptr(), None, None, x.data_ptr(), 32, 64, 64, 64, 0, None) == t._lib.E_INVALID   # M < 64
+    assert lib.tfsc_k_gemm_tc(x.data_ptr(), x.data_ptr(), None, None, x.data_ptr(), 64, 40, 64, 64, 0, None) == t._lib.E_INVALID   # N % 32
+
+
 @pytest.mark.parametrize("h,c,kh,stride,pad,cout", [(16, 3, 7, 2, 3, 8), (14, 16, 3, 1, 1, 24), (14, 16, 3, 2, 1, 24), (9, 5, 1, 2, 0, 7)])
 def test_conv_as_im2col_gemm_matches_torch(h, c, kh, stride, pad, cout):
     torch = _torch()

@@ -3,8 +3,8 @@
 //   im2col_nhwc   NHWC activations -> [B*OH*OW, KH*KW*C (padded to x4)] patch matrix (conv = im2col + GEMM with
 //                 the TF HWIO kernel flattened to [KH*KW*Cin, Cout]; 1x1/stride-1 convs skip it)
 //   maxpool / global average pool (NHWC), embedding gather + LayerNorm, residual LayerNorm, attention
-// These are the round-1 functional kernels (CUDA-core FFMA keeps the 1e-4 fp32 contract trivially); the
-// tcgen05 3xTF32 machinery of dense_tc.cu is the planned replacement for the GEMM.
+// launch_gemm dispatches to the tcgen05 3xTF32 GEMM of gemm_tc.cu when the shape allows (M >= 64, N % 32 == 0,
+// K >= 32); gemm_f32_kernel (CUDA-core FFMA, exact fp32) covers the rest (small M, N = 1000 / 2 heads, conv1's K).
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -136,7 +136,7 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, const 
 static bool gemm_tc_enabled() {  // TFSC_GEMM_TC=0 forces the CUDA-core GEMM
   static int v = [] {
     const char* e = getenv("TFSC_GEMM_TC");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : 1;
   }();
   return v != 0;
 }
