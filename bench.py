@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--dims", type=int, nargs="*", default=None, help="override model dims (debug only)")
     ap.add_argument("--workload", default="mlp", choices=["mlp", "resnet50"],
                     help="mlp = BASELINE configs[2] shard (default, the headline); resnet50 = configs[1] (100 ResNet-50 per GPU, "
-                         "32 HBM-resident, LRU paging in the loop) -- an extra line, functional CUDA-core conv path")
+                         "32 HBM-resident, LRU paging in the loop) -- an extra line")
     ap.add_argument("--replica-pick", default="balanced", choices=["balanced", "hot-spread", "random", "first"],
                     help="replica choice among the ring's GetN candidates (reference: random)")
     return ap.parse_args()
@@ -501,7 +501,7 @@ def run_b200(args):
         tf_peak = json.load(open(peaks_path)).get("bf16_tflops_sustained", 1405.4) if os.path.exists(peaks_path) else 1400.0
         tfl = 8.2e9 * n_req_all / world / (elapsed_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": round(tfl, 2), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(tfl / tf_peak, 5), "traffic": None,
-                "kernel": "gemm_f32_kernel (im2col + CUDA-core fp32 GEMM; round-1 functional conv path, not on tcgen05 yet)",
+                "kernel": "gemm_tc_kernel (im2col + tcgen05 3xTF32 GEMM; CUDA-core gemm_f32_kernel for M < 64 / N % 32 != 0 layers)",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)", "note": "8.2 GFLOP per 224x224 image"}
         workload = (f"BASELINE configs[1]: {args.models_per_gpu} ResNet-50 (v1.5, 25.5 M params, {model_bytes} B) per GPU, Zipf alpha=1.0, "
                     f"HBM cache holds {max_conc} models (serving.maxConcurrentModels), host tier holds all, 1 image per request")
