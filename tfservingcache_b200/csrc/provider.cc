@@ -93,6 +93,8 @@ std::shared_ptr<HostModel> DiskModelProvider::load_model(const std::string& name
   std::string mtxt;
   if (!read_file(src + "/tfsc_model.json", &mtxt)) {
     *err = "model " + name + ": " + src + "/tfsc_model.json not readable (not a tfsc-b200 bundle)";
+    if (access((src + "/saved_model.pb").c_str(), R_OK) == 0)
+      *err += "; a TensorFlow SavedModel is present: convert it with `python -m tfservingcache_b200.savedmodel " + base_dir_ + "`";
     return nullptr;
   }
   Json mj;
