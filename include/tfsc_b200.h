@@ -212,6 +212,10 @@ int tfsc_k_affine(const float* x, float* y, int64_t n, const float* a, const flo
 int tfsc_k_dense(const float* x, const float* w, const float* b, float* y, int rows, int k, int n, int relu,
                  float* workspace, size_t workspace_bytes, void* stream);                                    /* X2 */
 size_t tfsc_k_dense_workspace(int rows, int k, int n);
+/* tfsc_k_dense with an explicit kernel choice: 0 auto, 1 LDG-stream SIMT only, 2 bulk-copy (TMA) ring for the <= 8-row
+ * passes, 3 tensor cores for every row count. Same arguments, workspace and results (fp32 summation order differs). */
+int tfsc_k_dense_variant(int variant, const float* x, const float* w, const float* b, float* y, int rows, int k, int n,
+                         int relu, float* workspace, size_t workspace_bytes, void* stream);
 /* X3: the tcgen05/TMEM (3xTF32) path alone, rows <= 64, n % 32 == 0, k % 4 == 0. tfsc_k_dense picks it
  * automatically for more than 8 rows; this entry exists for parity tests and roofline timing. */
 int tfsc_k_dense_tc(const float* x, const float* w, const float* b, float* y, int rows, int k, int n, int relu,

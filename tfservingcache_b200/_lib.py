@@ -101,6 +101,7 @@ _sig("tfsc_kernel_launches", i64)
 _sig("tfsc_k_affine", C.c_int, vp, vp, i64, vp, vp, vp)
 _sig("tfsc_k_dense", C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp)
 _sig("tfsc_k_dense_workspace", sz, C.c_int, C.c_int, C.c_int)
+_sig("tfsc_k_dense_variant", C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp)
 _sig("tfsc_k_dense_tc", C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp)
 _sig("tfsc_k_gemm", C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp)
 _sig("tfsc_k_gemm_tc", C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp)

@@ -5,6 +5,7 @@
 // x staged in shared memory and broadcast, deterministic split-K reduction by the last CTA of
 // each column strip (no float atomics: bit-reproducible results).
 #include "kernels.h"
+#include "tc_ptx.cuh"
 
 #include <atomic>
 #include <cstdlib>
@@ -217,6 +218,203 @@ dense_stream_kernel(const float* __restrict__ x, const float* __restrict__ w, co
   }
 }
 
+// ------------------------------------------------------------------------- X2, bulk-copy ring ----
+// Same strip x K-split decomposition, workspace layout and deterministic fold as dense_stream_kernel, but W reaches
+// the SM through the async proxy: a producer warp issues one `cp.async.bulk` (TMA unit, no tensor map) per 2 KB
+// row segment into a ring of kBulkStages x 32 KB shared-memory stages guarded by full / empty mbarriers, so the bytes in
+// flight per SM (~128 KB) are not bounded by registers (the LDG variant holds 64 KB and reaches 84 % of the copy peak
+// at R = 8, profiles/r1_summary.md). 16 consumer warps = 128 float4 column groups x 4 k-lanes.
+// STATUS: compiled for sm_100a, not yet run on a GPU (written after the round's GPU budget was spent); selected only by
+// TFSC_DENSE_VARIANT=2 or tfsc_k_dense_variant(2, ...).
+constexpr int kBulkStageRows = 16;
+constexpr int kBulkStages = 5;
+constexpr int kBulkColGroups = kStripCols / 4;    // 128
+constexpr int kBulkKLanes = 4;
+constexpr int kBulkConsumers = kBulkColGroups * kBulkKLanes;   // 512
+constexpr int kBulkThreads = kBulkConsumers + 32;               // + one producer warp
+constexpr int kBulkRingFloats = kBulkStages * kBulkStageRows * kStripCols;
+constexpr size_t kBulkMaxSmem = 216 * 1024;
+
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(kBulkThreads, 1)
+dense_bulk_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ y, int rows, int K, int N, int relu, int splits, int chunk_k,
+                  unsigned int* __restrict__ counters, float* __restrict__ partials) {
+  extern __shared__ __align__(128) float smem_bulk[];
+  float* smem = smem_bulk;
+  float* ring = smem;                    // [kBulkStages][kBulkStageRows][kStripCols]
+  float* xs = smem + kBulkRingFloats;    // [chunk_k][R]
+  __shared__ __align__(8) uint64_t full[kBulkStages];
+  __shared__ __align__(8) uint64_t empty[kBulkStages];
+  __shared__ unsigned int s_last;
+
+  const int strip = blockIdx.x;
+  const int split = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int k_begin = split * chunk_k;
+  const int k_end = min(K, k_begin + chunk_k);
+  const int kc = max(0, k_end - k_begin);
+  const int strip_cols = min(kStripCols, N - strip * kStripCols);   // multiple of 8 (host guarantees N % 8 == 0)
+  const int n_stage = (kc + kBulkStageRows - 1) / kBulkStageRows;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kBulkStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kBulkConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int idx = tid; idx < kc * R; idx += kBulkThreads) {
+    const int r = idx / kc, k = idx - r * kc;
+    xs[k * R + r] = (r < rows) ? __ldg(x + (size_t)r * K + k_begin + k) : 0.f;
+  }
+  __syncthreads();
+
+  constexpr int kRowsPerLane = kBulkStageRows / kBulkKLanes;   // 4
+  float acc[R][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  const int cg = tid % kBulkColGroups;
+  const int kl = (tid / kBulkColGroups) % kBulkKLanes;
+
+  if (warp == kBulkConsumers / 32) {
+    // ---- producer: W rows [k_begin, k_end) x this strip's columns, 16 rows per stage
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    const uint32_t row_bytes = (uint32_t)strip_cols * 4u;
+    const float* src0 = w + (size_t)k_begin * N + (size_t)strip * kStripCols;
+    for (int it = 0; it < n_stage; ++it) {
+      const int s = it % kBulkStages;
+      if (it >= kBulkStages) mbar_wait(&empty[s], ((it / kBulkStages) - 1) & 1);
+      const int rows_here = min(kBulkStageRows, kc - it * kBulkStageRows);
+      if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)rows_here * row_bytes);
+      __syncwarp();
+      if (lane < rows_here)
+        bulk_copy_g2s(ring + ((size_t)s * kBulkStageRows + lane) * kStripCols,
+                      src0 + (size_t)(it * kBulkStageRows + lane) * N, row_bytes, &full[s], policy);
+    }
+  } else {
+    // ---- consumers
+    const bool col_ok = cg * 4 < strip_cols;
+    const uint32_t ring_s = smem_u32(ring) + (uint32_t)cg * 16u;
+    for (int it = 0; it < n_stage; ++it) {
+      const int s = it % kBulkStages;
+      mbar_wait(&full[s], (it / kBulkStages) & 1);
+      if (col_ok) {
+        const int kk0 = it * kBulkStageRows + kl;
+        const uint32_t base = ring_s + (uint32_t)((s * kBulkStageRows + kl) * kStripCols) * 4u;
+        float4 wv[kRowsPerLane];
+#pragma unroll
+        for (int j = 0; j < kRowsPerLane; ++j)
+          wv[j] = (kk0 + kBulkKLanes * j < kc) ? lds_f4(base + (uint32_t)(j * kBulkKLanes * kStripCols) * 4u)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kRowsPerLane; ++j) {
+          const int kk = min(kk0 + kBulkKLanes * j, kc - 1);   // clamped row pairs with wv = 0
+          const float* xr = xs + kk * R;
+          float xv[R];
+          if (R % 4 == 0) {
+#pragma unroll
+            for (int q = 0; q < R / 4; ++q) {
+              const float4 t = *reinterpret_cast<const float4*>(xr + 4 * q);
+              xv[4 * q + 0] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w;
+            }
+          } else if (R == 2) {
+            const float2 t = *reinterpret_cast<const float2*>(xr);
+            xv[0] = t.x; xv[1] = t.y;
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) xv[r] = xr[r];
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            acc[r][0] = fmaf(xv[r], wv[j].x, acc[r][0]);
+            acc[r][1] = fmaf(xv[r], wv[j].y, acc[r][1]);
+            acc[r][2] = fmaf(xv[r], wv[j].z, acc[r][2]);
+            acc[r][3] = fmaf(xv[r], wv[j].w, acc[r][3]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  }
+
+  // every full barrier has been waited on by every consumer: no copy is in flight, the ring can be reused
+  __syncthreads();
+  float* red = smem;  // [kBulkKLanes][R][kStripCols]  (64 KB at R = 8, inside the ring)
+  if (warp < kBulkConsumers / 32) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      *reinterpret_cast<float4*>(red + ((size_t)(kl * R + r) * kStripCols) + cg * 4) =
+          make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  }
+  __syncthreads();
+
+  constexpr int kVecPerRow = kStripCols / 4;
+  const float4* red4 = reinterpret_cast<const float4*>(red);
+  float4* my_partial = reinterpret_cast<float4*>(partials + ((size_t)(strip * splits + split) * R) * kStripCols);
+  for (int idx = tid; idx < R * kVecPerRow; idx += kBulkThreads) {
+    const int r = idx / kVecPerRow, c = idx - r * kVecPerRow;
+    float4 s = red4[(size_t)(0 * R + r) * kVecPerRow + c];
+#pragma unroll
+    for (int l = 1; l < kBulkKLanes; ++l) {
+      const float4 t = red4[(size_t)(l * R + r) * kVecPerRow + c];
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    if (splits == 1) {
+      const int col = strip * kStripCols + c * 4;
+      if (r < rows && col < N) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+        s.x += bv.x; s.y += bv.y; s.z += bv.z; s.w += bv.w;
+        if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+        *reinterpret_cast<float4*>(y + (size_t)r * N + col) = s;
+      }
+    } else {
+      my_partial[r * kVecPerRow + c] = s;
+    }
+  }
+  if (splits == 1) return;
+
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(&counters[strip], 1u);
+    s_last = (prev == (unsigned)splits - 1) ? 1u : 0u;
+    if (s_last) counters[strip] = 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float4* strip_partials = reinterpret_cast<const float4*>(partials + (size_t)strip * splits * R * kStripCols);
+  for (int idx = tid; idx < R * kVecPerRow; idx += kBulkThreads) {
+    const int r = idx / kVecPerRow, c = idx - r * kVecPerRow;
+    const int col = strip * kStripCols + c * 4;
+    if (r >= rows || col >= N) continue;
+    float4 s = __ldcg(strip_partials + (size_t)(0 * R + r) * kVecPerRow + c);
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 t = __ldcg(strip_partials + (size_t)(sp * R + r) * kVecPerRow + c);
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+    s.x += bv.x; s.y += bv.y; s.z += bv.z; s.w += bv.w;
+    if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+    *reinterpret_cast<float4*>(y + (size_t)r * N + col) = s;
+  }
+}
+
 // Generic fallback for shapes the streaming kernel does not cover (N % 8 != 0 or unaligned W):
 // one thread per output column, coalesced across columns. Small models only.
 __global__ void __launch_bounds__(256)
@@ -299,9 +497,44 @@ static cudaError_t launch_dense_r(const float* x, const float* w, const float* b
   return cudaGetLastError();
 }
 
+static bool bulk_fits(int R, const DensePlan& p) {
+  return (size_t)kBulkRingFloats * sizeof(float) + (size_t)p.chunk_k * R * sizeof(float) <= kBulkMaxSmem;
+}
+
+template <int R>
+static cudaError_t launch_dense_bulk_r(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n,
+                                       bool relu, void* workspace, const DensePlan& p, cudaStream_t s) {
+  const size_t smem = (size_t)kBulkRingFloats * sizeof(float) + (size_t)p.chunk_k * R * sizeof(float);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(dense_bulk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBulkMaxSmem);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  unsigned int* counters = static_cast<unsigned int*>(workspace);
+  size_t coff = ((size_t)p.strips * sizeof(unsigned int) + 255) & ~(size_t)255;
+  float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + coff);
+  dim3 grid(p.strips, p.splits);
+  dense_bulk_kernel<R><<<grid, kBulkThreads, smem, s>>>(x, w, bias, y, rows, k, n, relu ? 1 : 0, p.splits, p.chunk_k, counters,
+                                                        partials);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+static int dense_variant_default() {  // 0 = auto (LDG stream + tensor cores), 1 = LDG stream only, 2 = bulk ring, 3 = tc
+  static int v = [] {
+    const char* e = getenv("TFSC_DENSE_VARIANT");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
 cudaError_t launch_dense(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n,
-                         bool relu, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                         bool relu, void* workspace, size_t workspace_bytes, cudaStream_t s, int variant) {
   if (rows <= 0 || n <= 0) return cudaSuccess;
+  if (variant == 0) variant = dense_variant_default();
   const bool stream_ok = (n % 8 == 0) && ((reinterpret_cast<uintptr_t>(w) & 31) == 0) &&
                          ((reinterpret_cast<uintptr_t>(bias) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
                          k >= 1 && workspace && workspace_bytes >= dense_workspace_bytes(rows, k, n);
@@ -316,9 +549,10 @@ cudaError_t launch_dense(const float* x, const float* w, const float* bias, floa
   }
   const DensePlan p = plan_dense(k, n);
   int r_done = 0;
-  if (tc_min_rows() > 0 && rows >= tc_min_rows() && dense_tc_supported(rows > 64 ? 64 : rows, k, n, w, x, bias, y)) {
+  const int tc_rows = variant == 3 ? 1 : tc_min_rows();
+  if (variant != 1 && tc_rows > 0 && rows >= tc_rows && dense_tc_supported(rows > 64 ? 64 : rows, k, n, w, x, bias, y)) {
     // batches of more than 8 rows: one tensor-core pass per 64 rows instead of ceil(rows/8) SIMT passes
-    while (rows - r_done >= tc_min_rows()) {
+    while (rows - r_done >= tc_rows) {
       const int rr = rows - r_done < 64 ? rows - r_done : 64;
       cudaError_t e = launch_dense_tc(x + (size_t)r_done * k, w, bias, y + (size_t)r_done * n, rr, k, n, relu, workspace,
                                       workspace_bytes, s);
@@ -331,6 +565,14 @@ cudaError_t launch_dense(const float* x, const float* w, const float* bias, floa
     const float* xp = x + (size_t)r0 * k;
     float* yp = y + (size_t)r0 * n;
     cudaError_t e;
+    if (variant == 2 && bulk_fits(rr <= 2 ? rr : (rr <= 4 ? 4 : 8), p)) {
+      if (rr == 1) e = launch_dense_bulk_r<1>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+      else if (rr == 2) e = launch_dense_bulk_r<2>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+      else if (rr <= 4) e = launch_dense_bulk_r<4>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+      else e = launch_dense_bulk_r<8>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+      if (e != cudaSuccess) return e;
+      continue;
+    }
     if (rr == 1) e = launch_dense_r<1>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
     else if (rr == 2) e = launch_dense_r<2>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
     else if (rr <= 4) e = launch_dense_r<4>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);

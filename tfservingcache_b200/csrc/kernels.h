@@ -17,7 +17,9 @@ cudaError_t launch_affine(const float* x, float* y, int64_t n, const float* a, c
 // counters are maintained by the kernel itself (self-resetting).
 size_t dense_workspace_bytes(int rows, int k, int n);
 cudaError_t launch_dense(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n,
-                         bool relu, void* workspace, size_t workspace_bytes, cudaStream_t s);
+                         bool relu, void* workspace, size_t workspace_bytes, cudaStream_t s, int variant = 0);
+// variant: 0 auto (TFSC_DENSE_VARIANT, default LDG stream for <= 8 rows + tensor cores above), 1 LDG stream only,
+// 2 bulk-copy (TMA) ring for the <= 8-row passes (tensor cores above, as in auto), 3 tensor cores for every row count
 
 // X3: tcgen05/TMEM 3xTF32 path for 9..64 rows per pass (dense_tc.cu)
 bool dense_tc_supported(int rows, int k, int n, const float* w, const float* x, const float* bias, const float* y);
