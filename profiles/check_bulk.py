@@ -36,12 +36,14 @@ for (K, N) in [(64, 8), (100, 520), (1000, 512), (777, 1032), (4096, 4096), (921
             if relu:
                 ref = ref.clamp_min(0)
             y1 = run(1, x, w, b, relu, ws, ws_bytes)
-            y2 = run(2, x, w, b, relu, ws, ws_bytes)
-            y2b = run(2, x, w, b, relu, ws, ws_bytes)     # second launch: self-resetting counters, determinism
             e1 = (y1.double() - ref).abs().max().item()
-            e2 = (y2.double() - ref).abs().max().item()
-            out["parity"].append({"K": K, "N": N, "rows": rows, "relu": relu, "err_ldg": e1, "err_bulk": e2,
-                                  "deterministic": bool(torch.equal(y2, y2b)), "ok": bool(e2 < 2e-4 and torch.equal(y2, y2b))})
+            for variant in (2, 4):
+                y2 = run(variant, x, w, b, relu, ws, ws_bytes)
+                y2b = run(variant, x, w, b, relu, ws, ws_bytes)     # second launch: self-resetting counters, determinism
+                e2 = (y2.double() - ref).abs().max().item()
+                out["parity"].append({"K": K, "N": N, "rows": rows, "relu": relu, "variant": variant, "err_ldg": e1, "err_bulk": e2,
+                                      "deterministic": bool(torch.equal(y2, y2b)),
+                                      "ok": bool(e2 < 2e-4 and torch.equal(y2, y2b))})
             del x, w, b, ws
 bad = [p for p in out["parity"] if not p["ok"]]
 print(f"parity cases {len(out['parity'])} bad {len(bad)}", bad[:5])
@@ -54,7 +56,7 @@ for rows in (1, 2, 4, 8):
     y = torch.empty(rows, N, device="cuda")
     ws_bytes = lib.tfsc_k_dense_workspace(rows, K, N)
     ws = torch.zeros(ws_bytes // 4 + 64, device="cuda")
-    for variant in (1, 2):
+    for variant in (1, 2, 4):
         iters = 12
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
         torch.cuda.synchronize()

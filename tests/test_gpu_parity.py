@@ -47,7 +47,7 @@ def test_k_affine(n):
 
 
 # ---- X2 -------------------------------------------------------------------------------------
-def _dense(x, w, b, relu):
+def _dense(x, w, b, relu, variant=None):
     torch = _torch()
     rows, k = x.shape
     n = w.shape[1]
@@ -57,8 +57,12 @@ def _dense(x, w, b, relu):
     yd = torch.full((rows, n), float("nan"), device="cuda")
     for _ in range(2):  # twice: the split-K arrival counters must self-reset
         yd.fill_(float("nan"))
-        t._lib.check(t._lib.lib.tfsc_k_dense(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), yd.data_ptr(), rows, k, n,
-                                              1 if relu else 0, ws.data_ptr(), ws_bytes, None))
+        if variant is None:
+            t._lib.check(t._lib.lib.tfsc_k_dense(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), yd.data_ptr(), rows, k, n,
+                                                  1 if relu else 0, ws.data_ptr(), ws_bytes, None))
+        else:
+            t._lib.check(t._lib.lib.tfsc_k_dense_variant(variant, xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), yd.data_ptr(), rows,
+                                                          k, n, 1 if relu else 0, ws.data_ptr(), ws_bytes, None))
         torch.cuda.synchronize()
     return yd.cpu().numpy()
 
@@ -72,6 +76,23 @@ def test_k_dense_matches_oracle(rows, k, n):
     b = rng.standard_normal(n).astype(np.float32)
     for relu in (False, True):
         got = _dense(x, w, b, relu)
+        ref = x.astype(np.float64) @ w.astype(np.float64) + b
+        if relu:
+            ref = np.maximum(ref, 0)
+        assert not np.isnan(got).any()
+        assert _close(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("variant", [1, 2, 4])   # LDG stream, bulk-copy (TMA) ring with 8 / 4 k-lanes
+@pytest.mark.parametrize("rows", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("k,n", [(64, 8), (100, 520), (777, 1032), (4096, 4096), (20000, 64)])
+def test_k_dense_variants_match_oracle(variant, rows, k, n):
+    rng = np.random.default_rng(variant * 31 + rows * 7919 + k + n)
+    x = rng.standard_normal((rows, k)).astype(np.float32)
+    w = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    for relu in (False, True):
+        got = _dense(x, w, b, relu, variant)
         ref = x.astype(np.float64) @ w.astype(np.float64) + b
         if relu:
             ref = np.maximum(ref, 0)

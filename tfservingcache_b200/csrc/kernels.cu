@@ -222,16 +222,14 @@ dense_stream_kernel(const float* __restrict__ x, const float* __restrict__ w, co
 // Same strip x K-split decomposition, workspace layout and deterministic fold as dense_stream_kernel, but W reaches
 // the SM through the async proxy: a producer warp issues one `cp.async.bulk` (TMA unit, no tensor map) per 2 KB
 // row segment into a ring of kBulkStages x 32 KB shared-memory stages guarded by full / empty mbarriers, so the bytes in
-// flight per SM (~128 KB) are not bounded by registers (the LDG variant holds 64 KB and reaches 84 % of the copy peak
-// at R = 8, profiles/r1_summary.md). 16 consumer warps = 128 float4 column groups x 4 k-lanes.
-// STATUS: compiled for sm_100a, not yet run on a GPU (written after the round's GPU budget was spent); selected only by
-// TFSC_DENSE_VARIANT=2 or tfsc_k_dense_variant(2, ...).
+// flight per SM (~128 KB) are not bounded by registers. 16 consumer warps = 64 column groups x 8 k-lanes; a thread owns
+// the float4 column groups cg and cg + 64 of the strip (both LDS.128 conflict-free) and accumulates with packed
+// `fma.rn.f32x2` (FFMA2: two columns per issue slot, x broadcast from a scalar register), which halves the issue
+// pressure that bounded the first version of this kernel (profiles/r1_summary.md).
 constexpr int kBulkStageRows = 16;
 constexpr int kBulkStages = 5;
-constexpr int kBulkColGroups = kStripCols / 4;    // 128
-constexpr int kBulkKLanes = 4;
-constexpr int kBulkConsumers = kBulkColGroups * kBulkKLanes;   // 512
-constexpr int kBulkThreads = kBulkConsumers + 32;               // + one producer warp
+constexpr int kBulkColGroups = kStripCols / 8;    // 64 threads across a strip, 2 x float4 each
+// k-lanes KL (template): 8 -> 512 consumer threads (+ producer warp = 17 warps, 96 registers each), 4 -> 256 (9 warps, 168)
 constexpr int kBulkRingFloats = kBulkStages * kBulkStageRows * kStripCols;
 constexpr size_t kBulkMaxSmem = 216 * 1024;
 
@@ -242,12 +240,50 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+// two adjacent fp32 columns as one 64-bit register pair
+__device__ __forceinline__ void lds_2x64(uint32_t saddr, uint64_t& lo, uint64_t& hi) {
+  asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(saddr));
+}
+__device__ __forceinline__ void ffma2(uint64_t& acc, float xs, uint64_t w2) {
+  uint64_t x2;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(x2) : "f"(xs));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(x2), "l"(w2));
+}
 
 template <int R>
-__global__ void __launch_bounds__(kBulkThreads, 1)
+__device__ __forceinline__ void bulk_row(uint64_t (&acc)[R][4], uint32_t wrow_saddr, const float* xr) {
+  uint64_t w0, w1, w2, w3;
+  lds_2x64(wrow_saddr, w0, w1);
+  lds_2x64(wrow_saddr + (kStripCols / 2) * 4u, w2, w3);
+  float xv[R];
+  if (R % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < R / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(xr + 4 * q);
+      xv[4 * q + 0] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w;
+    }
+  } else if (R == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(xr);
+    xv[0] = t.x; xv[1] = t.y;
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) xv[r] = xr[r];
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    ffma2(acc[r][0], xv[r], w0);
+    ffma2(acc[r][1], xv[r], w1);
+    ffma2(acc[r][2], xv[r], w2);
+    ffma2(acc[r][3], xv[r], w3);
+  }
+}
+
+template <int R, int KL>
+__global__ void __launch_bounds__(kBulkColGroups * KL + 32, 1)
 dense_bulk_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ y, int rows, int K, int N, int relu, int splits, int chunk_k,
                   unsigned int* __restrict__ counters, float* __restrict__ partials) {
+  constexpr int kBulkKLanes = KL, kBulkConsumers = kBulkColGroups * KL, kBulkThreads = kBulkConsumers + 32;
   extern __shared__ __align__(128) float smem_bulk[];
   float* smem = smem_bulk;
   float* ring = smem;                    // [kBulkStages][kBulkStageRows][kStripCols]
@@ -274,18 +310,13 @@ dense_bulk_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int idx = tid; idx < kc * R; idx += kBulkThreads) {
-    const int r = idx / kc, k = idx - r * kc;
-    xs[k * R + r] = (r < rows) ? __ldg(x + (size_t)r * K + k_begin + k) : 0.f;
-  }
-  __syncthreads();
+  __syncthreads();  // barriers initialised; the producer starts streaming W while the consumers stage x
 
-  constexpr int kRowsPerLane = kBulkStageRows / kBulkKLanes;   // 4
-  float acc[R][4];
+  uint64_t acc[R][4];
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0ull;
   const int cg = tid % kBulkColGroups;
   const int kl = (tid / kBulkColGroups) % kBulkKLanes;
 
@@ -306,46 +337,28 @@ dense_bulk_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
                       src0 + (size_t)(it * kBulkStageRows + lane) * N, row_bytes, &full[s], policy);
     }
   } else {
-    // ---- consumers
-    const bool col_ok = cg * 4 < strip_cols;
+    // ---- consumers: stage x[:, k_begin:k_end] transposed (xs[k][r]) behind a consumer-only named barrier, then k-lane
+    // kl takes rows kl, kl + KL, ... of every stage. Columns >= strip_cols of a partial last strip are never copied:
+    // their sums are garbage and are discarded by the column guards of the epilogue.
+    for (int idx = tid; idx < kc * R; idx += kBulkConsumers) {
+      const int r = idx / kc, k = idx - r * kc;
+      xs[k * R + r] = (r < rows) ? __ldg(x + (size_t)r * K + k_begin + k) : 0.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(kBulkConsumers) : "memory");
     const uint32_t ring_s = smem_u32(ring) + (uint32_t)cg * 16u;
     for (int it = 0; it < n_stage; ++it) {
       const int s = it % kBulkStages;
       mbar_wait(&full[s], (it / kBulkStages) & 1);
-      if (col_ok) {
-        const int kk0 = it * kBulkStageRows + kl;
-        const uint32_t base = ring_s + (uint32_t)((s * kBulkStageRows + kl) * kStripCols) * 4u;
-        float4 wv[kRowsPerLane];
+      const int kk0 = it * kBulkStageRows + kl;
+      const uint32_t base = ring_s + (uint32_t)((s * kBulkStageRows + kl) * kStripCols) * 4u;
+      if (it * kBulkStageRows + kBulkStageRows <= kc) {
 #pragma unroll
-        for (int j = 0; j < kRowsPerLane; ++j)
-          wv[j] = (kk0 + kBulkKLanes * j < kc) ? lds_f4(base + (uint32_t)(j * kBulkKLanes * kStripCols) * 4u)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < kBulkStageRows / KL; ++j)
+          bulk_row<R>(acc, base + (uint32_t)(j * KL * kStripCols) * 4u, xs + (size_t)(kk0 + j * KL) * R);
+      } else {
 #pragma unroll
-        for (int j = 0; j < kRowsPerLane; ++j) {
-          const int kk = min(kk0 + kBulkKLanes * j, kc - 1);   // clamped row pairs with wv = 0
-          const float* xr = xs + kk * R;
-          float xv[R];
-          if (R % 4 == 0) {
-#pragma unroll
-            for (int q = 0; q < R / 4; ++q) {
-              const float4 t = *reinterpret_cast<const float4*>(xr + 4 * q);
-              xv[4 * q + 0] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w;
-            }
-          } else if (R == 2) {
-            const float2 t = *reinterpret_cast<const float2*>(xr);
-            xv[0] = t.x; xv[1] = t.y;
-          } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r) xv[r] = xr[r];
-          }
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            acc[r][0] = fmaf(xv[r], wv[j].x, acc[r][0]);
-            acc[r][1] = fmaf(xv[r], wv[j].y, acc[r][1]);
-            acc[r][2] = fmaf(xv[r], wv[j].z, acc[r][2]);
-            acc[r][3] = fmaf(xv[r], wv[j].w, acc[r][3]);
-          }
-        }
+        for (int j = 0; j < kBulkStageRows / KL; ++j)
+          if (kk0 + j * KL < kc) bulk_row<R>(acc, base + (uint32_t)(j * KL * kStripCols) * 4u, xs + (size_t)(kk0 + j * KL) * R);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
@@ -354,12 +367,14 @@ dense_bulk_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
 
   // every full barrier has been waited on by every consumer: no copy is in flight, the ring can be reused
   __syncthreads();
-  float* red = smem;  // [kBulkKLanes][R][kStripCols]  (64 KB at R = 8, inside the ring)
+  float* red = smem;  // [kBulkKLanes][R][kStripCols]  (128 KB at R = 8, inside the ring)
   if (warp < kBulkConsumers / 32) {
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      *reinterpret_cast<float4*>(red + ((size_t)(kl * R + r) * kStripCols) + cg * 4) =
-          make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    for (int r = 0; r < R; ++r) {
+      float* dst = red + ((size_t)(kl * R + r) * kStripCols) + cg * 4;
+      *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(acc[r][0], acc[r][1]);
+      *reinterpret_cast<ulonglong2*>(dst + kStripCols / 2) = make_ulonglong2(acc[r][2], acc[r][3]);
+    }
   }
   __syncthreads();
 
@@ -404,6 +419,7 @@ dense_bulk_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     const int col = strip * kStripCols + c * 4;
     if (r >= rows || col >= N) continue;
     float4 s = __ldcg(strip_partials + (size_t)(0 * R + r) * kVecPerRow + c);
+#pragma unroll 8
     for (int sp = 1; sp < splits; ++sp) {
       const float4 t = __ldcg(strip_partials + (size_t)(sp * R + r) * kVecPerRow + c);
       s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
@@ -501,7 +517,7 @@ static bool bulk_fits(int R, const DensePlan& p) {
   return (size_t)kBulkRingFloats * sizeof(float) + (size_t)p.chunk_k * R * sizeof(float) <= kBulkMaxSmem;
 }
 
-template <int R>
+template <int R, int KL>
 static cudaError_t launch_dense_bulk_r(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n,
                                        bool relu, void* workspace, const DensePlan& p, cudaStream_t s) {
   const size_t smem = (size_t)kBulkRingFloats * sizeof(float) + (size_t)p.chunk_k * R * sizeof(float);
@@ -509,7 +525,7 @@ static cudaError_t launch_dense_bulk_r(const float* x, const float* w, const flo
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(dense_bulk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBulkMaxSmem);
+    cudaError_t e = cudaFuncSetAttribute(dense_bulk_kernel<R, KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBulkMaxSmem);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
@@ -517,13 +533,13 @@ static cudaError_t launch_dense_bulk_r(const float* x, const float* w, const flo
   size_t coff = ((size_t)p.strips * sizeof(unsigned int) + 255) & ~(size_t)255;
   float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + coff);
   dim3 grid(p.strips, p.splits);
-  dense_bulk_kernel<R><<<grid, kBulkThreads, smem, s>>>(x, w, bias, y, rows, k, n, relu ? 1 : 0, p.splits, p.chunk_k, counters,
+  dense_bulk_kernel<R, KL><<<grid, kBulkColGroups * KL + 32, smem, s>>>(x, w, bias, y, rows, k, n, relu ? 1 : 0, p.splits, p.chunk_k, counters,
                                                         partials);
   g_launches++;
   return cudaGetLastError();
 }
 
-static int dense_variant_default() {  // 0 = auto (LDG stream + tensor cores), 1 = LDG stream only, 2 = bulk ring, 3 = tc
+static int dense_variant_default() {  // 0 = auto (LDG stream + tensor cores), 1 = LDG stream only, 2 / 4 = bulk ring (8 / 4 k-lanes), 3 = tc
   static int v = [] {
     const char* e = getenv("TFSC_DENSE_VARIANT");
     return e ? atoi(e) : 0;
@@ -565,11 +581,18 @@ cudaError_t launch_dense(const float* x, const float* w, const float* bias, floa
     const float* xp = x + (size_t)r0 * k;
     float* yp = y + (size_t)r0 * n;
     cudaError_t e;
-    if (variant == 2 && bulk_fits(rr <= 2 ? rr : (rr <= 4 ? 4 : 8), p)) {
-      if (rr == 1) e = launch_dense_bulk_r<1>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
-      else if (rr == 2) e = launch_dense_bulk_r<2>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
-      else if (rr <= 4) e = launch_dense_bulk_r<4>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
-      else e = launch_dense_bulk_r<8>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+    if ((variant == 2 || variant == 4) && bulk_fits(rr <= 2 ? rr : (rr <= 4 ? 4 : 8), p)) {
+      if (variant == 2) {
+        if (rr == 1) e = launch_dense_bulk_r<1, 8>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+        else if (rr == 2) e = launch_dense_bulk_r<2, 8>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+        else if (rr <= 4) e = launch_dense_bulk_r<4, 8>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+        else e = launch_dense_bulk_r<8, 8>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+      } else {
+        if (rr == 1) e = launch_dense_bulk_r<1, 4>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+        else if (rr == 2) e = launch_dense_bulk_r<2, 4>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+        else if (rr <= 4) e = launch_dense_bulk_r<4, 4>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+        else e = launch_dense_bulk_r<8, 4>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);
+      }
       if (e != cudaSuccess) return e;
       continue;
     }
