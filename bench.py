@@ -162,10 +162,12 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx, self.windows = [], None, gpu_index, []
+    def __init__(self, gpu_index, enabled=True):
+        self.rows, self.proc, self.idx, self.windows, self.enabled = [], None, gpu_index, [], enabled
 
     def start(self):
+        if not self.enabled:   # one nvidia-smi loop per box (local rank 0), as in the profiling recipe: eight concurrent
+            return             # loops each polling all eight GPUs perturb the very kernels they are meant to watch
         try:
             # all GPUs of the box are sampled (rank 0 only): a multi-GPU run can be slowed by one throttled device
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
@@ -184,6 +186,8 @@ class ClockSampler:
         self.windows.append((t0, t1))
 
     def stop(self):
+        if not self.enabled:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "per_gpu": []}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -222,8 +226,8 @@ class NvmlSampler:
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, gpu_index):
-        self.idx, self.rows, self.windows, self.ok, self._stop = gpu_index, [], [], False, False
+    def __init__(self, gpu_index, period_s=0.02):
+        self.idx, self.rows, self.windows, self.ok, self._stop, self.period_s = gpu_index, [], [], False, False, period_s
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -250,7 +254,7 @@ class NvmlSampler:
                 self.rows.append((time.time(), sm, pw, rs))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(self.period_s)
 
     def mark(self, t0, t1):
         self.windows.append((t0, t1))
@@ -354,8 +358,12 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # the request trace of every value-region step is grouped before the clock starts: the timed loop is route ->
+    # ensure-resident -> predict launches only, not numpy bookkeeping of the synthetic trace
+    pre_groups = {s: step_groups(wl, rank, s, tick_global) for s in range(W + K)}
+
     def device_step(step):
-        mine, groups = step_groups(wl, rank, step, tick_global)
+        mine, groups = pre_groups[step] if step in pre_groups else step_groups(wl, rank, step, tick_global)
         if graph_man:
             # cache under pressure: one fetchModel per REQUEST in arrival order, so the LRU sees real recency
             # (hit / reload accounting as in cachemanager.go:91-152); page-ins run on the copy stream
@@ -374,9 +382,9 @@ def run_b200(args):
         device_step(s)
     barrier()
     flush.fill_(1)  # inputs (>= 1 GB of weights per launch) already exceed L2; flush once anyway
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=(local == 0))
     sampler.start()
-    nvml = NvmlSampler(local)   # every rank watches its own GPU
+    nvml = NvmlSampler(local, period_s=0.02 if world == 1 else 0.1)   # every rank watches its own GPU
     nvml.start()
     launches0 = _lib.lib.tfsc_kernel_launches()
     st0 = srv.stats()
