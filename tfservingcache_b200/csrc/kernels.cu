@@ -73,6 +73,13 @@ __device__ __forceinline__ float8 ld_stream(const float8* p) {
   return r;
 }
 
+// Programmatic dependent launch (TFSC_PDL=1, bulk-ring variant only for now): a dense pass may begin while the previous kernel of the stream drains its
+// split-K tail. `pdl_trigger` lets the next grid start launching; `pdl_wait` blocks until every prerequisite grid has
+// completed and flushed (both are no-ops for a kernel launched without the attribute). Everything that depends on the
+// previous kernel (x, the shared split-K workspace, y) is touched only after pdl_wait; W never depends on it.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Workspace layout: [strips] uint32 arrival counters (self-resetting), then partial sums
 // float[strips][splits][R][kStripCols].
 template <int R>
@@ -311,6 +318,7 @@ dense_bulk_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();  // barriers initialised; the producer starts streaming W while the consumers stage x
+  pdl_trigger();
 
   uint64_t acc[R][4];
 #pragma unroll
@@ -336,10 +344,12 @@ dense_bulk_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
         bulk_copy_g2s(ring + ((size_t)s * kBulkStageRows + lane) * kStripCols,
                       src0 + (size_t)(it * kBulkStageRows + lane) * N, row_bytes, &full[s], policy);
     }
+    pdl_wait();
   } else {
     // ---- consumers: stage x[:, k_begin:k_end] transposed (xs[k][r]) behind a consumer-only named barrier, then k-lane
     // kl takes rows kl, kl + KL, ... of every stage. Columns >= strip_cols of a partial last strip are never copied:
     // their sums are garbage and are discarded by the column guards of the epilogue.
+    pdl_wait();  // x is the previous pass's y
     for (int idx = tid; idx < kc * R; idx += kBulkConsumers) {
       const int r = idx / kc, k = idx - r * kc;
       xs[k * R + r] = (r < rows) ? __ldg(x + (size_t)r * K + k_begin + k) : 0.f;
@@ -489,6 +499,29 @@ static int tc_min_rows() {  // rows per group from which the tensor-core path is
   return v;
 }
 
+static bool pdl_enabled() {
+  static bool v = [] {
+    const char* e = getenv("TFSC_PDL");
+    return e && atoi(e) != 0;
+  }();
+  return v;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <int R>
 static cudaError_t launch_dense_r(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n,
                                   bool relu, void* workspace, const DensePlan& p, cudaStream_t s) {
@@ -533,10 +566,10 @@ static cudaError_t launch_dense_bulk_r(const float* x, const float* w, const flo
   size_t coff = ((size_t)p.strips * sizeof(unsigned int) + 255) & ~(size_t)255;
   float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + coff);
   dim3 grid(p.strips, p.splits);
-  dense_bulk_kernel<R, KL><<<grid, kBulkColGroups * KL + 32, smem, s>>>(x, w, bias, y, rows, k, n, relu ? 1 : 0, p.splits, p.chunk_k, counters,
-                                                        partials);
+  cudaError_t le = launch_maybe_pdl(dense_bulk_kernel<R, KL>, grid, kBulkColGroups * KL + 32, smem, s, x, w, bias, y, rows, k, n,
+                                    relu ? 1 : 0, p.splits, p.chunk_k, counters, partials);
   g_launches++;
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 static int dense_variant_default() {  // 0 = auto (LDG stream + tensor cores), 1 = LDG stream only, 2 / 4 = bulk ring (8 / 4 k-lanes), 3 = tc
