@@ -36,7 +36,7 @@ def build_pool():
     from google.protobuf import wrappers_pb2, any_pb2  # noqa: F401  (well-known deps)
     pool = descriptor_pool.Default()
     fds = {}
-    for sub in ("core/framework", "core/lib/core", "serving"):
+    for sub in ("core/framework", "core/lib/core", "core/protobuf", "serving"):
         d = os.path.join(REF, sub)
         for fn in sorted(os.listdir(d)):
             if fn.endswith(".pb.go"):
@@ -57,7 +57,7 @@ def build_pool():
         done.add(name)
 
     for want in ("tensorflow_serving/apis/predict.proto", "tensorflow_serving/apis/get_model_status.proto",
-                 "tensorflow_serving/apis/model_management.proto"):
+                 "tensorflow_serving/apis/model_management.proto", "tensorflow_serving/apis/get_model_metadata.proto"):
         add(want)
     get = lambda full: message_factory.GetMessageClass(pool.FindMessageTypeByName(full))
     build_pool.get = get
@@ -136,6 +136,43 @@ def modelservice_golden():
     return out
 
 
+def metadata_golden():
+    """GetModelMetadata request / response (tfservingproxy.go:220-231 forwards them untouched) serialized from the
+    reference's embedded schema: SignatureDefMap packed into google.protobuf.Any under metadata["signature_def"]."""
+    build_pool()
+    get = build_pool.get
+    Req, Resp = get("tensorflow.serving.GetModelMetadataRequest"), get("tensorflow.serving.GetModelMetadataResponse")
+    SigMap = get("tensorflow.serving.SignatureDefMap")
+    out = {"cases": []}
+    r = Req(); r.model_spec.name = "half_plus_two"; r.model_spec.version.value = 123; r.metadata_field.append("signature_def")
+    out["request"] = {"name": "half_plus_two", "version": 123, "fields": ["signature_def"],
+                      "b64": base64.b64encode(r.SerializeToString(deterministic=True)).decode()}
+    r2 = Req(); r2.model_spec.name = "m0001"; r2.metadata_field.append("signature_def")
+    out["request_no_version"] = {"name": "m0001", "version": None, "fields": ["signature_def"],
+                                 "b64": base64.b64encode(r2.SerializeToString(deterministic=True)).decode()}
+    for name, version, in_key, in_dtype, in_dims, out_key, out_dims in [
+            ("half_plus_two", 123, "x", 1, [-1], "y", [-1]),
+            ("m0001", 1, "x", 1, [-1, 9216], "y", [-1, 9216]),
+            ("bert", 7, "input_ids", 3, [-1, 128], "logits", [-1, 2])]:
+        sm = SigMap()
+        sd = sm.signature_def["serving_default"]
+        for key, dtype, dims, target in ((in_key, in_dtype, in_dims, sd.inputs), (out_key, 1, out_dims, sd.outputs)):
+            ti = target[key]
+            ti.name = key + ":0"
+            ti.dtype = dtype
+            for d in dims:
+                ti.tensor_shape.dim.add().size = d
+        sd.method_name = "tensorflow/serving/predict"
+        resp = Resp()
+        resp.model_spec.name = name
+        resp.model_spec.version.value = version
+        resp.metadata["signature_def"].type_url = "type.googleapis.com/tensorflow.serving.SignatureDefMap"
+        resp.metadata["signature_def"].value = sm.SerializeToString(deterministic=True)
+        out["cases"].append({"name": name, "version": version, "input": [in_key, in_dtype, in_dims], "output": [out_key, 1, out_dims],
+                             "b64": base64.b64encode(resp.SerializeToString(deterministic=True)).decode()})
+    return out
+
+
 def ring_golden():
     from oracle import ring
     out = {"crc": {k: ring.crc32_ieee(k.encode()) for k in
@@ -188,4 +225,5 @@ if __name__ == "__main__":
     json.dump(ring_golden(), open(os.path.join(here, "ring_golden.json"), "w"), indent=1)
     json.dump(trace_golden(), open(os.path.join(here, "trace_golden.json"), "w"), indent=1)
     json.dump(modelservice_golden(), open(os.path.join(here, "modelservice_golden.json"), "w"), indent=1)
+    json.dump(metadata_golden(), open(os.path.join(here, "metadata_golden.json"), "w"), indent=1)
     print("golden fixtures written")

@@ -129,3 +129,24 @@ def test_tfserving_facade_model_service(endpoints, golden):
     code, msg = tfs_wire.decode_reload_config_response(reload_cfg(tfs_wire.encode_reload_config_request([("zzz", "/models/zzz", "tensorflow", [1])])))
     assert code == 5 and "No matching model" in msg
     ch.close()
+
+
+def test_grpc_get_model_metadata(endpoints):
+    """PredictionService.GetModelMetadata (forwarded by tfservingproxy.go:220-231): signature_def map of the model."""
+    import grpc
+    from tfservingcache_b200 import tfs_wire
+    _srv, _, target = endpoints
+    ch = grpc.insecure_channel(target)
+    meta = ch.unary_unary("/tensorflow.serving.PredictionService/GetModelMetadata", request_serializer=lambda b: b,
+                          response_deserializer=lambda b: b)
+    want = tfs_wire.encode_get_model_metadata_response("m5", 1, {"serving_default": {
+        "inputs": {"x": ("x:0", 1, [-1, DIMS[0]])}, "outputs": {"y": ("y:0", 1, [-1, DIMS[-1]])},
+        "method_name": "tensorflow/serving/predict"}})
+    assert meta(tfs_wire.encode_get_model_metadata_request("m5", 1)) == want
+    with pytest.raises(grpc.RpcError) as e:
+        meta(tfs_wire.encode_get_model_metadata_request("nope", 1))
+    assert e.value.code() == grpc.StatusCode.NOT_FOUND
+    with pytest.raises(grpc.RpcError) as e:
+        meta(tfs_wire.encode_get_model_metadata_request("m5", 1, fields=("bogus",)))
+    assert e.value.code() == grpc.StatusCode.INVALID_ARGUMENT
+    ch.close()

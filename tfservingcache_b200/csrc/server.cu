@@ -610,8 +610,8 @@ int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const 
     if (rc < 0) return fail_http(http_for(rc), err);
     std::string dim = d.tmpl == Template::Affine ? "" : std::to_string(d.in_dim);
     std::string odim = d.tmpl == Template::Affine ? "" : std::to_string(d.out_dim);
-    auto tensor_info = [](const std::string& key, const std::string& last_dim) {
-      std::string t = "\"" + key + "\": {\"dtype\": \"DT_FLOAT\", \"tensor_shape\": {\"dim\": [{\"size\": \"-1\", \"name\": \"\"}";
+    auto tensor_info = [](const std::string& key, const std::string& last_dim, const char* dtype) {
+      std::string t = "\"" + key + "\": {\"dtype\": \"" + dtype + "\", \"tensor_shape\": {\"dim\": [{\"size\": \"-1\", \"name\": \"\"}";
       if (!last_dim.empty()) t += ", {\"size\": \"" + last_dim + "\", \"name\": \"\"}";
       t += "], \"unknown_rank\": false}, \"name\": \"" + key + ":0\"}";
       return t;
@@ -619,7 +619,8 @@ int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const 
     std::string b = "{\n\"model_spec\": {\"name\": ";
     json_escape(name, &b);
     b += ", \"signature_name\": \"\", \"version\": \"" + std::to_string(id.version) + "\"},\n\"metadata\": {\"signature_def\": {\"signature_def\": {\"serving_default\": {\"inputs\": {" +
-         tensor_info(d.input_name, dim) + "}, \"outputs\": {" + tensor_info(d.output_name, odim) +
+         tensor_info(d.input_name, dim, d.input_dtype == TFSC_DT_INT32 ? "DT_INT32" : "DT_FLOAT") + "}, \"outputs\": {" +
+         tensor_info(d.output_name, odim, "DT_FLOAT") +
          "}, \"method_name\": \"tensorflow/serving/predict\"}}}}\n}\n";
     *http_status = 200;
     set_resp(b, resp, resp_len);

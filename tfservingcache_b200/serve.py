@@ -9,6 +9,7 @@ PredictRequest is never re-marshalled (the reference unmarshals + re-marshals it
 """
 from __future__ import annotations
 
+import json
 import sys
 import threading
 from concurrent import futures
@@ -151,13 +152,36 @@ def make_grpc_server(srv: Server, port: int, max_msg: int = 16 * 1024 * 1024, wo
             return tfs_wire.encode_reload_config_response(-e.code if -17 < e.code < 0 else 13, str(e))
         return tfs_wire.encode_reload_config_response()
 
+    def get_model_metadata(request: bytes, context):
+        # PredictionService.GetModelMetadata (tfservingproxy.go:220-231): same fetchModel path as Predict, answered
+        # from the model manifest; the only metadata field TF-Serving knows is "signature_def"
+        try:
+            name, version, fields = tfs_wire.decode_get_model_metadata_request(request)
+        except Exception as e:
+            context.abort(grpc.StatusCode.INVALID_ARGUMENT, str(e))
+        if not fields or any(f != "signature_def" for f in fields):
+            context.abort(grpc.StatusCode.INVALID_ARGUMENT,
+                          "Metadata field " + (next((f for f in fields if f != "signature_def"), "") or "<none>") + " is not supported"
+                          if fields else "GetModelMetadataRequest must specify at least one metadata_field")
+        v = 0 if version is None else version      # clientForSpec: a missing version is "0" (tfservingproxy.go:246-250)
+        status, body = srv.rest_handle("GET", f"/v1/models/{name}/versions/{v}/metadata", b"")
+        if status != 200:
+            msg = body.decode(errors="replace")
+            try:
+                msg = json.loads(msg).get("error", msg)
+            except ValueError:
+                pass
+            context.abort(grpc.StatusCode.NOT_FOUND if status == 404 else grpc.StatusCode.INTERNAL, msg)
+        return tfs_wire.encode_get_model_metadata_response(name, version, tfs_wire.signatures_from_rest_metadata(json.loads(body)))
+
     health_status = {"serving": True}
 
     def health_check(request: bytes, context):
         return b"\x08\x01" if health_status["serving"] else b"\x08\x02"  # HealthCheckResponse{status}
 
-    methods = {"Predict": grpc.unary_unary_rpc_method_handler(predict, ident, ident)}
-    for m in ("Classify", "Regress", "MultiInference", "GetModelMetadata"):
+    methods = {"Predict": grpc.unary_unary_rpc_method_handler(predict, ident, ident),
+               "GetModelMetadata": grpc.unary_unary_rpc_method_handler(get_model_metadata, ident, ident)}
+    for m in ("Classify", "Regress", "MultiInference"):
         methods[m] = grpc.unary_unary_rpc_method_handler(unsupported(m), ident, ident)
     server = grpc.server(futures.ThreadPoolExecutor(max_workers=workers),
                          options=[("grpc.max_receive_message_length", max_msg), ("grpc.max_send_message_length", max_msg)])

@@ -201,3 +201,70 @@ def decode_reload_config_response(buf: bytes):
                 elif f2 == 2 and wt2 == 2:
                     msg = v2.decode()
     return code, msg
+
+
+# ---- PredictionService.GetModelMetadata (tfservingproxy.go:220-231 forwards it by model_spec) ------------------
+# GetModelMetadataRequest{model_spec=1, metadata_field=2 rep string}; GetModelMetadataResponse{model_spec=1,
+# metadata=2 map<string, google.protobuf.Any{type_url=1, value=2}>}; SignatureDefMap{signature_def=1 map<string,
+# SignatureDef{inputs=1 map<string,TensorInfo>, outputs=2 map, method_name=3}>}; TensorInfo{name=1, dtype=2,
+# tensor_shape=3 TensorShapeProto{dim=2{size=1}}} (proto/tensorflow/serving/get_model_metadata.pb.go:27,68-70,117-121;
+# proto/tensorflow/core/protobuf/meta_graph.pb.go:658-662,698,937-948)
+SIGNATURE_DEF_TYPE_URL = "type.googleapis.com/tensorflow.serving.SignatureDefMap"
+DT_BY_NAME = {"DT_FLOAT": 1, "DT_INT32": 3, "DT_INT64": 9}
+
+
+def decode_get_model_metadata_request(buf: bytes):
+    """-> (name, version or None, [metadata_field])"""
+    spec, fields = b"", []
+    for f, wt, v in _fields(buf):
+        if f == 1 and wt == 2:
+            spec = v
+        elif f == 2 and wt == 2:
+            fields.append(v.decode())
+    name, version = decode_get_model_status_request(_ld(1, spec))
+    return name, version, fields
+
+
+def encode_get_model_metadata_request(name: str, version: int | None, fields=("signature_def",)) -> bytes:
+    return encode_get_model_status_request(name, version) + b"".join(_ld(2, f.encode()) for f in fields)
+
+
+def _tensor_info(name: str, dtype: int, dims) -> bytes:
+    shape = b"".join(_ld(2, _vi(1, d) if d else b"") for d in dims)
+    return (_ld(1, name.encode()) if name else b"") + (_vi(2, dtype) if dtype else b"") + _ld(3, shape)
+
+
+def _map_entry(field: int, key: str, value: bytes) -> bytes:
+    return _ld(field, (_ld(1, key.encode()) if key else b"") + _ld(2, value))
+
+
+def encode_signature_def_map(signatures: dict) -> bytes:
+    """signatures: {sig_name: {"inputs": {key: (tensor_name, dtype, dims)}, "outputs": {...}, "method_name": str}}.
+    Map entries are written in key order (what protobuf's deterministic serialization does)."""
+    out = b""
+    for sig in sorted(signatures):
+        sd = signatures[sig]
+        body = b"".join(_map_entry(1, k, _tensor_info(*sd["inputs"][k])) for k in sorted(sd["inputs"]))
+        body += b"".join(_map_entry(2, k, _tensor_info(*sd["outputs"][k])) for k in sorted(sd["outputs"]))
+        if sd.get("method_name"):
+            body += _ld(3, sd["method_name"].encode())
+        out += _map_entry(1, sig, body)
+    return out
+
+
+def encode_get_model_metadata_response(name: str, version: int | None, signatures: dict) -> bytes:
+    spec = _ld(1, name.encode()) if name else b""
+    if version is not None:
+        spec += _ld(2, _vi(1, version) if version else b"")
+    any_msg = _ld(1, SIGNATURE_DEF_TYPE_URL.encode()) + _ld(2, encode_signature_def_map(signatures))
+    return _ld(1, spec) + _map_entry(2, "signature_def", any_msg)
+
+
+def signatures_from_rest_metadata(doc: dict) -> dict:
+    """The REST /metadata JSON (server.cu, TF-Serving's layout) -> the structure encode_signature_def_map takes."""
+    out = {}
+    for sig, sd in doc["metadata"]["signature_def"]["signature_def"].items():
+        conv = lambda m: {k: (v.get("name", ""), DT_BY_NAME.get(v.get("dtype", ""), 0),
+                              [int(d["size"]) for d in v.get("tensor_shape", {}).get("dim", [])]) for k, v in m.items()}  # noqa: E731
+        out[sig] = {"inputs": conv(sd.get("inputs", {})), "outputs": conv(sd.get("outputs", {})), "method_name": sd.get("method_name", "")}
+    return out
