@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "../../tfservingcache_b200/csrc/arena.h"
 #include "../../tfservingcache_b200/csrc/json.h"
 #include "../../tfservingcache_b200/csrc/lru.h"
 #include "../../tfservingcache_b200/csrc/model.h"
@@ -100,6 +101,32 @@ int main(int argc, char** argv) {
     ModelId id{"m" + std::to_string(rng() % 30), (int64_t)(rng() % 3)};
     if (rng() % 2) lru.put(id, CachedModel{id, "p", (int64_t)(rng() % 400)}); else lru.get(id, nullptr);
     if (lru.current_size() < 0) { fprintf(stderr, "negative LRU size\n"); return 1; }
+  }
+  // HBM arena allocator: random alloc / release, blocks never overlap, accounting exact, full coalescing at the end
+  {
+    Arena a; a.init(1 << 20, 1024);
+    std::vector<std::pair<size_t, size_t>> live;  // offset, rounded length
+    for (int i = 0; i < 20000; ++i) {
+      if (live.empty() || rng() % 3) {
+        size_t bytes = 1 + rng() % (96 << 10), off = 0;
+        if (a.alloc(bytes, &off)) {
+          size_t len = (bytes + 1023) / 1024 * 1024;
+          if (off % 1024 || off + len > a.capacity()) { fprintf(stderr, "arena: bad block\n"); return 1; }
+          for (auto& b : live)
+            if (off < b.first + b.second && b.first < off + len) { fprintf(stderr, "arena: overlap\n"); return 1; }
+          live.push_back({off, len});
+        } else if (a.largest_free() >= (bytes + 1023) / 1024 * 1024) { fprintf(stderr, "arena: refused a fitting block\n"); return 1; }
+      } else {
+        size_t k = rng() % live.size();
+        a.release(live[k].first);
+        a.release(live[k].first);  // double release is ignored
+        live[k] = live.back(); live.pop_back();
+      }
+      size_t sum = 0; for (auto& b : live) sum += b.second;
+      if (sum != a.used() || live.size() != a.blocks()) { fprintf(stderr, "arena: accounting\n"); return 1; }
+    }
+    for (auto& b : live) a.release(b.first);
+    if (a.used() != 0 || a.largest_free() != a.capacity()) { fprintf(stderr, "arena: not coalesced\n"); return 1; }
   }
   printf("fuzz ok: %d iterations, %ld requests decoded, %ld json parsed, %ld manifests accepted\n", iters, decoded, jsons, manifests);
   return 0;
