@@ -126,6 +126,13 @@ int tfsc_grpc_model_spec(const void* req, size_t len, char* model_name, size_t n
  * (fixed: recursive byte size). */
 int tfsc_disk_find_version_dir(const char* base_dir, const char* model_name, int64_t version, char* buf, size_t cap);
 int64_t tfsc_disk_model_size(const char* base_dir, const char* model_name, int64_t version);
+/* TensorFlow SavedModel ingestion without TensorFlow. The disk provider imports a version directory that
+ * holds `saved_model.pb` + `variables/variables.{index,data-*}` (and no tfsc_model.json) on the fly when the model is
+ * fetched; this entry does the same conversion offline and writes tfsc_model.json + weights.bin into out_dir (may equal
+ * version_dir). Recognised graphs: y = a*x + b (half_plus_two) and MatMul + BiasAdd (+ Relu) chains; anything else is
+ * TFSC_E_INVALID with the offending node in tfsc_last_error(). Needs no GPU. */
+int tfsc_savedmodel_convert(const char* version_dir, const char* out_dir);
+uint32_t tfsc_crc32c(const void* data, size_t len);   /* CRC-32C (Castagnoli), the tensor-bundle / table checksum */
 
 /* ---------------------------------------------------------------- server (a6,a8,a10,X) ------
  * One server = the cache tier + proxy tier of cmd/taskhandler/main.go:45-113 for the GPUs of

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <random>
 #include <string>
 #include <vector>
@@ -13,7 +14,9 @@
 #include "../../tfservingcache_b200/csrc/lru.h"
 #include "../../tfservingcache_b200/csrc/model.h"
 #include "../../tfservingcache_b200/csrc/parse.h"
+#include "../../tfservingcache_b200/csrc/provider.h"
 #include "../../tfservingcache_b200/csrc/ring.h"
+#include "../../tfservingcache_b200/csrc/savedmodel.h"
 #include "../../tfservingcache_b200/csrc/wire.h"
 
 using namespace tfsc;
@@ -128,6 +131,41 @@ int main(int argc, char** argv) {
     for (auto& b : live) a.release(b.first);
     if (a.used() != 0 || a.largest_free() != a.capacity()) { fprintf(stderr, "arena: not coalesced\n"); return 1; }
   }
+  // SavedModel importer: argv[2] = a well-formed fixture directory written by the pytest wrapper; every file is mutated in a
+  // scratch copy (argv[3]) and re-imported: errors are fine, out-of-bounds access is not
+  long sm_ok = 0, sm_runs = 0;
+  if (argc > 3) {
+    const std::string src = argv[2], dst = argv[3];
+    auto slurp = [](const std::string& p) { std::string o; FILE* f = fopen(p.c_str(), "rb"); if (f) { char b[4096]; size_t n; while ((n = fread(b, 1, sizeof b, f)) > 0) o.append(b, n); fclose(f); } return o; };
+    auto spit = [](const std::string& p, const std::string& d) { FILE* f = fopen(p.c_str(), "wb"); if (f) { fwrite(d.data(), 1, d.size(), f); fclose(f); } };
+    const char* files[3] = {"/saved_model.pb", "/variables/variables.index", "/variables/variables.data-00000-of-00001"};
+    std::string good_f[3];
+    for (int k = 0; k < 3; ++k) { good_f[k] = slurp(src + files[k]); spit(dst + files[k], good_f[k]); }
+    SavedModelBundle sb; std::string err;
+    if (!savedmodel_import(dst, &sb, &err)) { fprintf(stderr, "savedmodel fixture failed: %s\n", err.c_str()); return 1; }
+    // the disk provider imports the same directory on the fly when it holds no tfsc_model.json (argv[4] = base dir
+    // with the fixture linked as <base>/m/00000007)
+    if (argc > 4) {
+      DiskModelProvider prov(argv[4]);
+      HostAllocFn alloc = [](size_t n, std::function<void(void*, size_t)>* rel) { *rel = [](void* q, size_t) { free(q); }; return malloc(n); };
+      std::string perr;
+      auto hm = prov.load_model("m", 7, alloc, &perr);
+      if (!hm || hm->desc.tmpl != Template::Mlp || hm->desc.layers.size() != 2 || hm->desc.layers[0].in != 12 || hm->desc.layers[1].out != 5 ||
+          hm->bytes != sb.weights.size() || memcmp(hm->data, sb.weights.data(), hm->bytes) != 0) {
+        fprintf(stderr, "disk provider SavedModel import failed: %s\n", perr.c_str());
+        return 1;
+      }
+      if (prov.load_model("m", 8, alloc, &perr) || perr != "No matching model found") { fprintf(stderr, "expected no match\n"); return 1; }
+    }
+    for (int i = 0; i < 1500; ++i) {
+      const int k = i % 3;
+      spit(dst + files[k], (i % 5 == 0) ? random_bytes(rng() % 300) : mutate(good_f[k]));
+      SavedModelBundle b2; ++sm_runs;
+      if (savedmodel_import(dst, &b2, &err)) ++sm_ok;
+      spit(dst + files[k], good_f[k]);
+    }
+  }
+  printf("savedmodel: %ld of %ld mutated imports accepted\n", sm_ok, sm_runs);
   printf("fuzz ok: %d iterations, %ld requests decoded, %ld json parsed, %ld manifests accepted\n", iters, decoded, jsons, manifests);
   return 0;
 }

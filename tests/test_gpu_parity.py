@@ -278,6 +278,34 @@ def test_grpc_predict_wire_roundtrip(golden):
         assert st["proxy_requests_grpc"] == 5 and st["proxy_failures_grpc"] == 3
 
 
+def test_disk_provider_serves_tensorflow_savedmodel_trees(tmp_path):
+    """a model repository of TensorFlow SavedModel directories (saved_model.pb + variables/), as
+    TF-Serving would load them, served without conversion step: the disk provider imports graph + variables on the fly.
+    half_plus_two graph shape (y = a*x + b, deploy/docker-compose/readme.md:40-42) and a Keras-style dense MLP."""
+    _torch()
+    from savedmodel_fixtures import _mlp_fixture, write_bundle, write_saved_model
+    repo = tmp_path
+    d = repo / "saved_model_half_plus_two_cpu" / "00000123"
+    os.makedirs(d)
+    write_bundle(str(d / "variables" / "variables"), {"a": np.array(0.5, np.float32), "b": np.array(2.0, np.float32)})
+    write_saved_model(str(d / "saved_model.pb"),
+                      [("x", "Placeholder", []), ("a", "VariableV2", []), ("a/read", "Identity", ["a"]), ("b", "VariableV2", []),
+                       ("b/read", "Identity", ["b"]), ("Mul", "Mul", ["a/read", "x"]), ("y", "Add", ["Mul", "b/read"])],
+                      ("x", "x:0", "y", "y:0"))
+    tensors = _mlp_fixture(repo / "mlp" / "7", np.random.default_rng(21), (48, 64, 16))
+    cfg = {"modelProvider.type": "diskProvider", "modelProvider.diskProvider.baseDir": str(repo), "modelCache.size": 1 << 20,
+           "serving.maxConcurrentModels": 2, "gpu.devices": [0], "gpu.arenaBytes": 1 << 20}
+    with t.Server(cfg) as srv:
+        st, body = srv.rest_handle("POST", "/v1/models/saved_model_half_plus_two_cpu/versions/00000123:predict",
+                                   b'{"instances": [1.0, 2.0, 5.0]}')
+        assert st == 200 and json.loads(body) == {"predictions": [2.5, 3.0, 4.5]}
+        x = np.random.default_rng(22).standard_normal((5, 48)).astype(np.float32)
+        y = srv.predict("mlp", "7", x)
+        h = np.maximum(x.astype(np.float64) @ tensors["dense/kernel"] + tensors["dense/bias"], 0)
+        ref = h @ tensors["dense_1/kernel"] + tensors["dense_1/bias"]
+        assert y.shape == (5, 16) and _close(y, ref) <= TOL
+
+
 def test_half_plus_two_rest_and_grpc_known_answer(tmp_path, golden):
     """The only end-to-end known answer in the reference (deploy/docker-compose/readme.md:25-42),
     through the disk provider, REST and gRPC, version directory 00000123."""

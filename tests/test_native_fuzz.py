@@ -16,13 +16,21 @@ def test_host_parsers_survive_fuzzing_under_asan_ubsan(tmp_path):
         pytest.skip("g++ not available")
     exe = str(tmp_path / "fuzz_host")
     srcs = [os.path.join(ROOT, "tests", "native", "fuzz_host.cc")] + [os.path.join(CSRC, f) for f in
-            ("common.cc", "ring.cc", "lru.cc", "parse.cc", "wire.cc", "model.cc")]
-    cmd = [gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-o", exe] + srcs
+            ("common.cc", "ring.cc", "lru.cc", "parse.cc", "wire.cc", "model.cc", "savedmodel.cc", "provider.cc")]
+    cmd = [gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-o", exe] + srcs + ["-lpthread"]
     build = subprocess.run(cmd, capture_output=True, text=True)
     if build.returncode != 0 and "sanitize" in (build.stderr or "").lower() and "cannot find" in build.stderr.lower():
         pytest.skip("sanitizer runtime not installed")
     assert build.returncode == 0, build.stderr[-3000:]
-    run = subprocess.run([exe, "20000"], capture_output=True, text=True, timeout=300,
+    # a well-formed SavedModel fixture for the importer leg (written by the helpers of tests/test_savedmodel.py)
+    import numpy as np
+    from savedmodel_fixtures import _mlp_fixture
+    fixture, scratch = tmp_path / "sm_fixture", tmp_path / "sm_scratch"
+    _mlp_fixture(fixture, np.random.default_rng(0), (12, 20, 5))
+    os.makedirs(scratch / "variables")
+    os.makedirs(tmp_path / "base" / "m")
+    os.symlink(fixture, tmp_path / "base" / "m" / "00000007")
+    run = subprocess.run([exe, "20000", str(fixture), str(scratch), str(tmp_path / "base")], capture_output=True, text=True, timeout=300,
                          env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=1", UBSAN_OPTIONS="print_stacktrace=1"))
     assert run.returncode == 0, (run.stdout + run.stderr)[-4000:]
     assert "fuzz ok" in run.stdout

@@ -12,86 +12,7 @@ from oracle import models
 from tfservingcache_b200 import savedmodel as sm
 
 
-def _vi(v):
-    out = bytearray()
-    while True:
-        b = v & 0x7F
-        v >>= 7
-        if v:
-            out.append(b | 0x80)
-        else:
-            out.append(b)
-            return bytes(out)
-
-
-def _ld(f, p):
-    return _vi((f << 3) | 2) + _vi(len(p)) + p
-
-
-def _v(f, v):
-    return _vi(f << 3) + _vi(v)
-
-
-def _block(entries, restart_interval=2):
-    out, restarts, last = bytearray(), [], b""
-    for i, (k, v) in enumerate(entries):
-        shared = 0
-        if i % restart_interval == 0:
-            restarts.append(len(out))
-        else:
-            while shared < min(len(last), len(k)) and last[shared] == k[shared]:
-                shared += 1
-        out += _vi(shared) + _vi(len(k) - shared) + _vi(len(v)) + k[shared:] + v
-        last = k
-    for r in restarts:
-        out += struct.pack("<I", r)
-    out += struct.pack("<I", len(restarts))
-    return bytes(out)
-
-
-def write_table(path, items, block_items=3):
-    items = sorted(items.items())
-    data, index = bytearray(), []
-    for i in range(0, len(items), block_items):
-        chunk = items[i:i + block_items]
-        blk = _block(chunk)
-        off = len(data)
-        data += blk + b"\x00" + struct.pack("<I", sm.mask_crc(sm.crc32c(blk + b"\x00")))
-        index.append((chunk[-1][0], _vi(off) + _vi(len(blk))))
-    meta = _block([])
-    meta_off = len(data)
-    data += meta + b"\x00" + struct.pack("<I", sm.mask_crc(sm.crc32c(meta + b"\x00")))
-    idx = _block(index, restart_interval=1)
-    idx_off = len(data)
-    data += idx + b"\x00" + struct.pack("<I", sm.mask_crc(sm.crc32c(idx + b"\x00")))
-    footer = _vi(meta_off) + _vi(len(meta)) + _vi(idx_off) + _vi(len(idx))
-    footer += b"\x00" * (40 - len(footer)) + struct.pack("<Q", sm.TABLE_MAGIC)
-    open(path, "wb").write(bytes(data) + footer)
-
-
-def write_bundle(prefix, tensors):
-    os.makedirs(os.path.dirname(prefix), exist_ok=True)
-    blob, items = bytearray(), {b"": _v(1, 1) + _ld(3, _v(1, 1))}   # num_shards=1, little endian, version{producer=1}
-    for name, arr in tensors.items():
-        raw = np.ascontiguousarray(arr, np.float32).tobytes()
-        shape = b"".join(_ld(2, _v(1, d)) for d in arr.shape)
-        entry = _v(1, 1) + _ld(2, shape) + (_v(4, len(blob)) if len(blob) else b"") + _v(5, len(raw)) + \
-            _vi((6 << 3) | 5) + struct.pack("<I", sm.mask_crc(sm.crc32c(raw)))
-        items[name.encode()] = entry
-        blob += raw
-    open(prefix + ".data-00000-of-00001", "wb").write(bytes(blob))
-    write_table(prefix + ".index", items)
-
-
-def write_saved_model(path, nodes, signature):
-    graph = b"".join(_ld(1, _ld(1, n.encode()) + _ld(2, op.encode()) + b"".join(_ld(3, i.encode()) for i in ins)) for n, op, ins in nodes)
-    in_key, in_t, out_key, out_t = signature
-
-    def tinfo(k, t):
-        return _ld(1, k.encode()) + _ld(2, _ld(1, t.encode()) + _v(2, 1))
-    sig = _ld(1, tinfo(in_key, in_t)) + _ld(2, tinfo(out_key, out_t)) + _ld(3, b"tensorflow/serving/predict")
-    meta = _ld(2, graph) + _ld(5, _ld(1, b"serving_default") + _ld(2, sig))
-    open(path, "wb").write(_v(1, 1) + _ld(2, meta))
+from savedmodel_fixtures import _mlp_fixture, write_bundle, write_saved_model  # noqa: E402
 
 
 def test_crc32c_known_answer():
@@ -185,3 +106,80 @@ def test_import_tree_converts_in_place(tmp_path):
     oman, blob = models.load_bundle(str(tmp_path / "hp2" / "00000002"))
     assert models.forward(oman, blob, np.array([2.0], np.float32)).tolist() == [3.0]
     assert sm.import_tree(str(tmp_path)) == [(str(tmp_path / "bad" / "1"), res[str(tmp_path / "bad" / "1")])]   # idempotent
+
+
+# ---- native importer (csrc/savedmodel.cc through the C ABI): same fixtures, byte-identical bundles -------------------
+def _native_convert(src, dst):
+    from tfservingcache_b200 import _lib
+    os.makedirs(dst, exist_ok=True)
+    return _lib.lib.tfsc_savedmodel_convert(str(src).encode(), str(dst).encode())
+
+
+def test_native_crc32c_matches_python():
+    from tfservingcache_b200 import _lib
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 7, 8, 9, 63, 64, 1000, 4097):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert _lib.lib.tfsc_crc32c(data, len(data)) == sm.crc32c(data)
+    assert _lib.lib.tfsc_crc32c(b"123456789", 9) == 0xE3069283
+
+
+def test_native_importer_matches_python_importer(tmp_path):
+    rng = np.random.default_rng(11)
+    cases = []
+    d = tmp_path / "hp2" / "00000123"
+    os.makedirs(d)
+    write_bundle(str(d / "variables" / "variables"), {"a": np.array(0.5, np.float32), "b": np.array(2.0, np.float32)})
+    write_saved_model(str(d / "saved_model.pb"),
+                      [("x", "Placeholder", []), ("a", "VariableV2", []), ("a/read", "Identity", ["a"]), ("b", "VariableV2", []),
+                       ("b/read", "Identity", ["b"]), ("Mul", "Mul", ["a/read", "x"]), ("y", "Add", ["Mul", "b/read"])],
+                      ("x", "x:0", "y", "y:0"))
+    cases.append(d)
+    for i, (dims, relu_last) in enumerate([((6, 10, 4), False), ((5, 7), True), ((33, 64, 17, 9, 3), False), ((300, 260), False)]):
+        d = tmp_path / f"mlp{i}" / "1"
+        _mlp_fixture(d, rng, dims, relu_last)
+        cases.append(d)
+    for d in cases:
+        py, nat = tmp_path / "py" / d.parent.name, tmp_path / "nat" / d.parent.name
+        sm.convert(str(d), str(py))
+        assert _native_convert(d, nat) == 0
+        assert open(py / "weights.bin", "rb").read() == open(nat / "weights.bin", "rb").read()
+        assert json.load(open(py / "tfsc_model.json")) == json.load(open(nat / "tfsc_model.json"))
+
+
+def test_native_importer_rejects_bad_inputs(tmp_path):
+    from tfservingcache_b200 import _lib
+    rng = np.random.default_rng(5)
+    assert _native_convert(tmp_path / "missing", tmp_path / "o0") == _lib.E_NOT_FOUND
+    d = tmp_path / "weird" / "1"
+    os.makedirs(d)
+    write_bundle(str(d / "variables" / "variables"), {"a": np.array(1.0, np.float32)})
+    write_saved_model(str(d / "saved_model.pb"), [("x", "Placeholder", []), ("y", "Softmax", ["x"])], ("x", "x:0", "y", "y:0"))
+    assert _native_convert(d, tmp_path / "o1") == _lib.E_INVALID and b"Softmax" in _lib.lib.tfsc_last_error()
+    # corrupted tensor data, corrupted index block, truncated files: an error, never a crash
+    d = tmp_path / "m" / "1"
+    _mlp_fixture(d, rng)
+    p = d / "variables" / "variables.data-00000-of-00001"
+    raw = bytearray(open(p, "rb").read())
+    raw[5] ^= 0x40
+    open(p, "wb").write(bytes(raw))
+    assert _native_convert(d, tmp_path / "o2") == _lib.E_INVALID and b"checksum" in _lib.lib.tfsc_last_error()
+    raw[5] ^= 0x40
+    open(p, "wb").write(bytes(raw))
+    assert _native_convert(d, tmp_path / "o3") == 0
+    idx = d / "variables" / "variables.index"
+    good = open(idx, "rb").read()
+    for cut in (0, 10, 47, len(good) - 1):
+        open(idx, "wb").write(good[:cut])
+        assert _native_convert(d, tmp_path / "o4") == _lib.E_INVALID
+    for pos in range(0, len(good), 7):
+        bad = bytearray(good)
+        bad[pos] ^= 0xFF
+        open(idx, "wb").write(bytes(bad))
+        assert _native_convert(d, tmp_path / "o5") in (0, _lib.E_INVALID)
+    open(idx, "wb").write(good)
+    pb = d / "saved_model.pb"
+    gpb = open(pb, "rb").read()
+    for cut in range(0, len(gpb), 11):
+        open(pb, "wb").write(gpb[:cut])
+        assert _native_convert(d, tmp_path / "o6") in (0, _lib.E_INVALID)

@@ -81,6 +81,8 @@ _sig("tfsc_parse_version", C.c_int, cp, C.POINTER(i64))
 _sig("tfsc_grpc_model_spec", C.c_int, vp, sz, C.c_char_p, sz, C.c_char_p, sz)
 _sig("tfsc_disk_find_version_dir", C.c_int, cp, cp, i64, C.c_char_p, sz)
 _sig("tfsc_disk_model_size", i64, cp, cp, i64)
+_sig("tfsc_savedmodel_convert", C.c_int, cp, cp)
+_sig("tfsc_crc32c", C.c_uint32, vp, sz)
 _sig("tfsc_server_create", vp, cp)
 _sig("tfsc_server_destroy", None, vp)
 _sig("tfsc_server_num_nodes", C.c_int, vp)

@@ -1,4 +1,5 @@
 #include "provider.h"
+#include "savedmodel.h"
 
 #include <dirent.h>
 #include <fcntl.h>
@@ -91,15 +92,35 @@ std::shared_ptr<HostModel> DiskModelProvider::load_model(const std::string& name
   std::string src;
   if (!find_src_path(base_dir_ + "/" + name, version, &src, err)) return nullptr;
   std::string mtxt;
-  if (!read_file(src + "/tfsc_model.json", &mtxt)) {
-    *err = "model " + name + ": " + src + "/tfsc_model.json not readable (not a tfsc-b200 bundle)";
-    if (access((src + "/saved_model.pb").c_str(), R_OK) == 0)
-      *err += "; a TensorFlow SavedModel is present: convert it with `python -m tfservingcache_b200.savedmodel " + base_dir_ + "`";
-    return nullptr;
-  }
   Json mj;
   auto m = std::make_shared<HostModel>();
   m->id = {name, version};
+  if (!read_file(src + "/tfsc_model.json", &mtxt)) {
+    if (!savedmodel_present(src)) {
+      *err = "model " + name + ": " + src + "/tfsc_model.json not readable (not a tfsc-b200 bundle)";
+      return nullptr;
+    }
+    // a TensorFlow SavedModel directory as TF-Serving would load it: import graph + variables on the fly
+    SavedModelBundle sb;
+    std::string ierr;
+    if (!savedmodel_import(src, &sb, &ierr)) {
+      *err = "model " + name + ": SavedModel import failed: " + ierr;
+      return nullptr;
+    }
+    if (!json_parse(sb.manifest_json, &mj, err) || !parse_manifest(mj, &m->desc, err)) return nullptr;
+    m->bytes = m->desc.weights_bytes;
+    if (sb.weights.size() < m->bytes) {
+      *err = "model " + name + ": imported weights shorter than manifest weights_bytes";
+      return nullptr;
+    }
+    m->data = alloc(m->bytes, &m->release);
+    if (!m->data) {
+      *err = "host allocation of " + std::to_string(m->bytes) + " bytes failed";
+      return nullptr;
+    }
+    memcpy(m->data, sb.weights.data(), m->bytes);
+    return m;
+  }
   if (!json_parse(mtxt, &mj, err) || !parse_manifest(mj, &m->desc, err)) return nullptr;
   std::string wpath = src + "/weights.bin";
   int fd = open(wpath.c_str(), O_RDONLY);
@@ -314,4 +335,24 @@ int64_t tfsc_disk_model_size(const char* base_dir, const char* model_name, int64
   if (s < 0) return tfsc::fail(TFSC_E_NOT_FOUND, "%s", err.c_str());
   return s;
 }
+
+int tfsc_savedmodel_convert(const char* version_dir, const char* out_dir) {
+  if (!version_dir || !out_dir) return tfsc::fail(TFSC_E_INVALID, "savedmodel_convert: bad arguments");
+  tfsc::SavedModelBundle sb;
+  std::string err;
+  if (!tfsc::savedmodel_present(version_dir)) return tfsc::fail(TFSC_E_NOT_FOUND, "%s/saved_model.pb not found", version_dir);
+  if (!tfsc::savedmodel_import(version_dir, &sb, &err)) return tfsc::fail(TFSC_E_INVALID, "%s", err.c_str());
+  auto put = [&](const std::string& path, const void* d, size_t n) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    bool ok = fwrite(d, 1, n, f) == n;
+    return fclose(f) == 0 && ok;
+  };
+  mkdir(out_dir, 0755);  // an existing directory is fine
+  if (!put(std::string(out_dir) + "/weights.bin", sb.weights.data(), sb.weights.size()) ||
+      !put(std::string(out_dir) + "/tfsc_model.json", sb.manifest_json.data(), sb.manifest_json.size()))
+    return tfsc::fail(TFSC_E_INTERNAL, "cannot write the bundle into %s", out_dir);
+  return 0;
+}
+uint32_t tfsc_crc32c(const void* data, size_t len) { return tfsc::crc32c(data, len); }
 }
