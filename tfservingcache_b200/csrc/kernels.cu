@@ -73,7 +73,7 @@ __device__ __forceinline__ float8 ld_stream(const float8* p) {
   return r;
 }
 
-// Programmatic dependent launch (TFSC_PDL=1, bulk-ring variant only for now): a dense pass may begin while the previous kernel of the stream drains its
+// Programmatic dependent launch (TFSC_PDL=1; separate instantiations, the default kernels are unchanged): a dense pass may begin while the previous kernel of the stream drains its
 // split-K tail. `pdl_trigger` lets the next grid start launching; `pdl_wait` blocks until every prerequisite grid has
 // completed and flushed (both are no-ops for a kernel launched without the attribute). Everything that depends on the
 // previous kernel (x, the shared split-K workspace, y) is touched only after pdl_wait; W never depends on it.
@@ -82,7 +82,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // Workspace layout: [strips] uint32 arrival counters (self-resetting), then partial sums
 // float[strips][splits][R][kStripCols].
-template <int R>
+template <int R, bool PDL = false>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_stream_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                     float* __restrict__ y, int rows, int K, int N, int relu, int splits, int chunk_k,
@@ -101,6 +101,10 @@ dense_stream_kernel(const float* __restrict__ x, const float* __restrict__ w, co
   const int k_end = min(K, k_begin + chunk_k);
   const int kc = max(0, k_end - k_begin);
 
+  if (PDL) {  // TFSC_PDL=1 instantiation only: let the next grid launch early, then wait for the previous one (x, workspace)
+    pdl_trigger();
+    pdl_wait();
+  }
   // stage x[:, k_begin:k_end] transposed into smem: xs[k][r]
   for (int idx = tid; idx < kc * R; idx += kThreads) {
     const int r = idx / kc, k = idx - r * kc;
@@ -540,6 +544,18 @@ static cudaError_t launch_dense_r(const float* x, const float* w, const float* b
   size_t coff = ((size_t)p.strips * sizeof(unsigned int) + 255) & ~(size_t)255;
   float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + coff);
   dim3 grid(p.strips, p.splits);
+  if (pdl_enabled()) {
+    static bool attr_set_pdl[64] = {};
+    if (!attr_set_pdl[dev & 63]) {
+      cudaError_t e = cudaFuncSetAttribute(dense_stream_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set_pdl[dev & 63] = true;
+    }
+    cudaError_t le = launch_maybe_pdl(dense_stream_kernel<R, true>, grid, kThreads, smem, s, x, w, bias, y, rows, k, n, relu ? 1 : 0,
+                                      p.splits, p.chunk_k, counters, partials);
+    g_launches++;
+    return le != cudaSuccess ? le : cudaGetLastError();
+  }
   dense_stream_kernel<R><<<grid, kThreads, smem, s>>>(x, w, bias, y, rows, k, n, relu ? 1 : 0, p.splits, p.chunk_k,
                                                       counters, partials);
   g_launches++;
