@@ -12,17 +12,19 @@ pytestmark = [pytest.mark.gpu,
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 PDL_SCRIPT = r"""
+import os
 import numpy as np, torch
 import tfservingcache_b200 as t
 lib = t._lib.lib
+VARIANTS = tuple(int(v) for v in os.environ.get('TFSC_TEST_VARIANTS', '1,2,4').split(','))
 rng = np.random.default_rng(0)
 worst = 0.0
-for (K, N) in [(64, 8), (100, 520), (777, 1032), (4096, 4096), (9216, 9216)]:
+for (K, N) in [(64, 8), (100, 520), (128, 64), (132, 260), (780, 1032), (2048 + 64, 512), (4096, 4096), (9216, 9216)]:
     for rows in (1, 3, 8):
         x = torch.randn(rows, K, device="cuda"); w = torch.randn(K, N, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
         ws_bytes = lib.tfsc_k_dense_workspace(rows, K, N); ws = torch.zeros(ws_bytes // 4 + 64, device="cuda")
         ref = (x.double() @ w.double() + b.double()).clamp_min(0)
-        for variant in (1, 2, 4):
+        for variant in VARIANTS:
             y = torch.full((rows, N), float("nan"), device="cuda")
             # back-to-back launches on one stream: with TFSC_PDL=1 each pass may start under the tail of the previous one
             for _ in range(6):
@@ -50,6 +52,15 @@ assert worst < 2e-4, worst
 @pytest.mark.parametrize("variant_env", ["0", "2", "4"])
 def test_programmatic_dependent_launch_keeps_results(variant_env):
     env = dict(os.environ, TFSC_PDL="1", TFSC_DENSE_VARIANT=variant_env, PYTHONPATH=ROOT)
+    run = subprocess.run([sys.executable, "-c", PDL_SCRIPT], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
+    assert "WORST" in run.stdout
+
+
+@pytest.mark.parametrize("pdl", ["0", "1"])
+def test_cluster_pair_dense_kernel(pdl):
+    """tfsc_k_dense_variant 5 (csrc/dense_cluster.cu): 2-CTA clusters, K halves meet in distributed shared memory."""
+    env = dict(os.environ, TFSC_PDL=pdl, TFSC_DENSE_VARIANT="5", TFSC_TEST_VARIANTS="5", PYTHONPATH=ROOT)
     run = subprocess.run([sys.executable, "-c", PDL_SCRIPT], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
     assert "WORST" in run.stdout

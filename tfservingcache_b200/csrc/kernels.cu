@@ -15,7 +15,8 @@ namespace tfsc {
 static std::atomic<int64_t> g_launches{0};
 extern std::atomic<int64_t> g_launches_tc;
 extern std::atomic<int64_t> g_launches_nn;
-int64_t kernel_launch_count() { return g_launches.load() + g_launches_tc.load() + g_launches_nn.load(); }
+extern std::atomic<int64_t> g_launches_cl;
+int64_t kernel_launch_count() { return g_launches.load() + g_launches_tc.load() + g_launches_nn.load() + g_launches_cl.load(); }
 
 // ------------------------------------------------------------------------------------ X1 ----
 __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n,
@@ -630,6 +631,11 @@ cudaError_t launch_dense(const float* x, const float* w, const float* bias, floa
     const float* xp = x + (size_t)r0 * k;
     float* yp = y + (size_t)r0 * n;
     cudaError_t e;
+    if (variant == 5 && dense_cluster_supported(rr, k, n, w, xp, bias, yp)) {
+      e = launch_dense_cluster(xp, w, bias, yp, rr, k, n, relu, s);
+      if (e != cudaSuccess) return e;
+      continue;
+    }
     if ((variant == 2 || variant == 4) && bulk_fits(rr <= 2 ? rr : (rr <= 4 ? 4 : 8), p)) {
       if (variant == 2) {
         if (rr == 1) e = launch_dense_bulk_r<1, 8>(xp, w, bias, yp, rr, k, n, relu, workspace, p, s);

@@ -19,13 +19,20 @@ size_t dense_workspace_bytes(int rows, int k, int n);
 cudaError_t launch_dense(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n,
                          bool relu, void* workspace, size_t workspace_bytes, cudaStream_t s, int variant = 0);
 // variant: 0 auto (TFSC_DENSE_VARIANT, default LDG stream for <= 8 rows + tensor cores above), 1 LDG stream only,
-// 2 bulk-copy (TMA) ring for the <= 8-row passes (tensor cores above, as in auto), 3 tensor cores for every row count
+// 2 / 4 bulk-copy (TMA) ring for the <= 8-row passes (tensor cores above, as in auto), 3 tensor cores for every row count,
+// 5 cluster-pair kernel for the <= 8-row passes (experimental)
 
 // X3: tcgen05/TMEM 3xTF32 path for 9..64 rows per pass (dense_tc.cu)
 bool dense_tc_supported(int rows, int k, int n, const float* w, const float* x, const float* bias, const float* y);
 size_t dense_tc_workspace_bytes(int k, int n);
 cudaError_t launch_dense_tc(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n,
                             bool relu, void* workspace, size_t workspace_bytes, cudaStream_t s);
+
+// X2, cluster-pair variant (dense_cluster.cu, EXPERIMENTAL, variant 5): two CTAs of a cluster split K and meet in
+// distributed shared memory -- no split-K workspace, no atomics. rows <= 8, n % 4 == 0, k % 4 == 0, k >= 128.
+bool dense_cluster_supported(int rows, int k, int n, const float* w, const float* x, const float* bias, const float* y);
+cudaError_t launch_dense_cluster(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n, bool relu,
+                                 cudaStream_t s);
 
 // X4/X5 building blocks (nn_kernels.cu): act 0 none / 1 relu / 2 gelu(erf)
 cudaError_t launch_gemm(const float* A, const float* B, const float* bias, const float* R, float* C, int M, int N, int K,

@@ -696,7 +696,7 @@ size_t tfsc_k_dense_workspace(int rows, int k, int n) { return dense_workspace_b
 int tfsc_k_dense_variant(int variant, const float* x, const float* w, const float* b, float* y, int rows, int k, int n,
                          int relu, float* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_device()) return rc;
-  if (variant < 0 || variant > 4) return fail(TFSC_E_INVALID, "dense: variant %d not in 0..4", variant);
+  if (variant < 0 || variant > 5) return fail(TFSC_E_INVALID, "dense: variant %d not in 0..5", variant);
   cudaError_t e = launch_dense(x, w, b, y, rows, k, n, relu != 0, workspace, workspace_bytes, (cudaStream_t)stream, variant);
   return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "dense(variant %d): %s", variant, cudaGetErrorString(e));
 }
