@@ -9,7 +9,8 @@ and the published algorithm of stathat.com/c/consistent v1.0.0 (go.mod:25; absen
 /root/reference, restated): 20 virtual points per member at crc32_ieee(str(i) + member), a
 map hash->member (later insert overwrites, remove deletes the point), ascending sorted hashes,
 lookup = first point strictly greater than crc32_ieee(key), wrapping to index 0.
-PARITY UNPINNED for absolute placements (see oracle/__init__.py).
+Pinned on the module's own published test vectors, recalled from the public source (see oracle/__init__.py and
+tests/test_oracle_pins.py::test_ring_reproduces_upstream_module_test_vectors).
 """
 from __future__ import annotations
 

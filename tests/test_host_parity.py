@@ -337,3 +337,35 @@ def test_balanced_picker_evens_out_keys_per_member():
     for key, gpu in list(bound.items())[:200]:              # sticky: a bound key keeps its member
         ids = [int(s.host[3:]) for s in c.find_node_for_key(key)]
         assert ids[pk.pick_ids(key, ids, 8)] == gpu
+
+
+def test_native_ring_reproduces_upstream_module_test_vectors():
+    """The C++ ring (csrc/ring.cc) against the known answers of stathat.com/c/consistent's own tests
+    (see tests/test_oracle_pins.py for their provenance)."""
+    import ctypes as C
+    from test_oracle_pins import UPSTREAM_GET, UPSTREAM_GET_AFTER_REMOVING_HIJKLMN, UPSTREAM_GETN, UPSTREAM_MEMBERS
+    lib = t._lib.lib
+    h = lib.tfsc_ring_new()
+
+    def set_members(ms):
+        arr = (C.c_char_p * len(ms))(*[m.encode() for m in ms])
+        assert lib.tfsc_ring_set(h, arr, len(ms)) >= 0
+
+    def get_n(key, n):
+        buf = C.create_string_buffer(1024)
+        cnt = lib.tfsc_ring_getn(h, key.encode(), n, buf, 1024)
+        assert cnt >= 0
+        return buf.value.decode().split("\n") if cnt else []
+
+    try:
+        set_members(UPSTREAM_MEMBERS)
+        assert lib.tfsc_ring_members(h) == 3 and lib.tfsc_ring_points(h) == 60
+        for key, want in UPSTREAM_GET:
+            assert get_n(key, 1) == [want]
+        for key, n, want in UPSTREAM_GETN:
+            assert get_n(key, n) == want
+        set_members(["abcdefg", "opqrstu"])
+        for key, want in UPSTREAM_GET_AFTER_REMOVING_HIJKLMN:
+            assert get_n(key, 1) == [want]
+    finally:
+        lib.tfsc_ring_free(h)

@@ -255,3 +255,28 @@ def test_create_model_config_groups_by_name():
     cfg = ocm.create_model_config(ms, "/models")
     assert [(c["name"], c["versions"], c["base_path"]) for c in cfg] == [("a", [1, 2], "/models/a"), ("b", [7], "/models/b")]
     assert all(c["model_platform"] == "tensorflow" for c in cfg)
+
+
+# ---- stathat.com/c/consistent v1.0.0 known answers --------------------------------------------------------------
+# The module is not vendored in the reference (go.mod:25) and cannot be fetched here. These are the expectations of its
+# own test-suite (consistent_test.go: TestGetMultiple, TestGetMultipleRemove, TestGetTwo, TestGetN, TestGetNLess,
+# TestGetNMore), quoted from memory of the public source -- not read from disk. The restatement reproduces every one of
+# them, which pins the vnode key format (strconv.Itoa(i) + member), the 20 replicas, CRC-32/IEEE and the clockwise walk.
+UPSTREAM_MEMBERS = ["abcdefg", "hijklmn", "opqrstu"]
+UPSTREAM_GET = [("ggg", "abcdefg"), ("hhh", "opqrstu"), ("iiiii", "hijklmn")]
+UPSTREAM_GET_AFTER_REMOVING_HIJKLMN = [("ggg", "abcdefg"), ("hhh", "opqrstu"), ("iiiii", "opqrstu")]
+UPSTREAM_GETN = [("99999999", 2, ["abcdefg", "hijklmn"]),               # TestGetTwo / TestGetNLess
+                 ("9999999", 3, ["opqrstu", "abcdefg", "hijklmn"]),     # TestGetN
+                 ("9999999", 5, ["opqrstu", "abcdefg", "hijklmn"])]     # TestGetNMore: n clamps to the member count
+
+
+def test_ring_reproduces_upstream_module_test_vectors():
+    c = ring.Consistent()
+    c.set(UPSTREAM_MEMBERS)
+    for key, want in UPSTREAM_GET:
+        assert c.get_n(key, 1) == [want]
+    for key, n, want in UPSTREAM_GETN:
+        assert c.get_n(key, n) == want
+    c.set(["abcdefg", "opqrstu"])
+    for key, want in UPSTREAM_GET_AFTER_REMOVING_HIJKLMN:
+        assert c.get_n(key, 1) == [want]
