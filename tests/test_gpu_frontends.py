@@ -150,3 +150,69 @@ def test_grpc_get_model_metadata(endpoints):
         meta(tfs_wire.encode_get_model_metadata_request("m5", 1, fields=("bogus",)))
     assert e.value.code() == grpc.StatusCode.INVALID_ARGUMENT
     ch.close()
+
+
+def _varint(v):
+    out = b""
+    while True:
+        b7 = v & 0x7F
+        v >>= 7
+        out += bytes([b7 | (0x80 if v else 0)])
+        if not v:
+            return out
+
+
+def test_request_shape_cannot_undersize_the_response(endpoints):
+    """ADVICE r1 (high): rows are derived from the element count, the response shape from the client's tensor_shape;
+    a [1, 2*in_dim] request is two rows and must be rejected, not written into a one-row buffer."""
+    import ctypes as C
+    srv, base, _ = endpoints
+    two_rows_as_one = np.random.default_rng(5).standard_normal((1, 2 * DIMS[0])).astype(np.float32)
+    st, body = _http(f"{base}/v1/models/m3/versions/1:predict", json.dumps({"instances": two_rows_as_one.tolist()}).encode())
+    assert st == 400 and b"does not match the model signature" in body
+    with pytest.raises(t.TfscError) as e:
+        srv.grpc_predict(wire.encode_predict_request("m3", 1, {"x": two_rows_as_one}))
+    assert e.value.code == t._lib.E_INVALID
+    # C ABI with an output buffer sized from the (wrong) shape the client claims: must fail, not overflow
+    with pytest.raises(t.TfscError) as e:
+        srv.predict("m3", "1", two_rows_as_one, out_capacity_elems=DIMS[-1])
+    assert e.value.code == t._lib.E_INVALID
+    # a flat vector of 2*in_dim elements is two rows: accepted, shape [2, out]
+    flat = two_rows_as_one.reshape(-1)
+    y = srv.predict("m3", "1", flat)
+    assert y.shape == (2, DIMS[-1]) and np.max(np.abs(y - _ref(3, flat.reshape(2, -1)))) <= 1e-4
+    # more than one input tensor is an error (the templates have one input), not silently ignored
+    tin = (t._lib.TfscTensor * 2)()
+    x = np.zeros((1, DIMS[0]), np.float32)
+    for i in range(2):
+        tin[i].dtype, tin[i].rank, tin[i].data, tin[i].nbytes = t._lib.DT_FLOAT, 2, x.ctypes.data, x.nbytes
+        tin[i].shape[0], tin[i].shape[1] = 1, DIMS[0]
+    yb = np.empty(DIMS[-1], np.float32)
+    tout = t._lib.TfscTensor()
+    tout.data, tout.nbytes = yb.ctypes.data, yb.nbytes
+    assert t._lib.lib.tfsc_predict(srv._h, b"m3", b"1", tin, 2, C.byref(tout), 1) == t._lib.E_INVALID
+
+
+def test_scalar_broadcast_is_bounded(endpoints):
+    """a ~30-byte request whose tensor_shape says 2^33 elements must be refused before anything is
+    allocated (and nothing may be thrown through the C ABI)."""
+    srv, _, _ = endpoints
+
+    def req(dim):
+        shape = b"\x12" + _varint(len(b"\x08" + _varint(dim))) + b"\x08" + _varint(dim)     # TensorShapeProto{dim{size}}
+        tensor = b"\x08\x01" + b"\x12" + _varint(len(shape)) + shape + b"\x2a\x04" + np.float32(1.5).tobytes()
+        entry = b"\x0a\x01x" + b"\x12" + _varint(len(tensor)) + tensor
+        spec = b"\x0a\x02m3" + b"\x12\x02\x08\x01"
+        return b"\x0a" + _varint(len(spec)) + spec + b"\x12" + _varint(len(entry)) + entry
+
+    for dim in (1 << 33, 1 << 62, (1 << 24) + 1):
+        with pytest.raises(t.TfscError) as e:
+            srv.grpc_predict(req(dim))
+        assert e.value.code == t._lib.E_INVALID
+    # the legitimate use still works: one value fills a [2, in] tensor
+    ok = wire.encode_predict_request("m3", 1, {"x": np.full((2, DIMS[0]), 1.5, np.float32)})
+    _spec, outs = wire.decode_predict_response(srv.grpc_predict(ok))
+    want = outs["y"]
+    small = req(DIMS[0])   # shape [in], one float_val -> broadcast
+    _spec, outs = wire.decode_predict_response(srv.grpc_predict(small))
+    assert np.max(np.abs(outs["y"].reshape(-1) - want[0])) <= 1e-6

@@ -280,6 +280,22 @@ def test_disk_provider_matches_prefix_zeros(tmp_path):
         p.find_src_path_for_model("nope", 1)
 
 
+def test_disk_provider_refuses_names_that_leave_base_dir(tmp_path):
+    """gRPC ModelSpec.name is not constrained by the REST regex: '..' / 'a/b' must not reach the file system."""
+    repo = tmp_path / "repo"
+    outside = tmp_path / "outside"
+    _dummy(str(repo), "inside", "1")
+    _dummy(str(tmp_path), "outside", "1")
+    p = t.DiskModelProvider(str(repo))
+    assert p.find_src_path_for_model("inside", 1).endswith("inside/1")
+    for bad in ("../outside", "..", ".", "inside/../inside", "", "a/b"):
+        with pytest.raises(FileNotFoundError):
+            p.find_src_path_for_model(bad, 1)
+        with pytest.raises(FileNotFoundError):
+            p.model_size(bad, 1)
+    assert outside.exists()
+
+
 # ---- config surface (cfg.go:10-66) ------------------------------------------------------------
 def test_config_yaml_and_env(tmp_path):
     cfgp = tmp_path / "config.yaml"

@@ -73,6 +73,7 @@ Node::~Node() {
   }
   for (auto& kv : stream_scratch_) cudaFree(kv.second.base);
   for (auto& r : retire_) cudaEventDestroy(r.ev);
+  drain_.clear();
   for (auto& kv : dev_)
     if (kv.second->ready) cudaEventDestroy(kv.second->ready);
   dev_.clear();
@@ -156,9 +157,24 @@ void Node::refresh_state_locked(DeviceModel* d) {
   }
 }
 
-void Node::release_locked(const std::shared_ptr<DeviceModel>& d) {
+void Node::release_locked(const std::shared_ptr<DeviceModel>& d_in) {
+  const std::shared_ptr<DeviceModel> d = d_in;  // the dev_ entry (possibly the caller's reference) is erased below
   if (!d->dptr) return;
-  if (!d->ready_seen && d->ready) cudaEventSynchronize(d->ready);  // page-in DMA must not outlive its source
+  if (!d->ready_seen && d->ready) {
+    // the page-in DMA must not outlive its source / its arena block. Never wait for it under mu_ (a multi-GB copy would
+    // stall every fetch / status call of the node): park the block as "draining", reap_locked() frees it once the
+    // copy-stream event has completed.
+    if (cudaEventQuery(d->ready) != cudaSuccess) {
+      cudaGetLastError();
+      if (!d->draining) {
+        d->draining = true;
+        drain_.push_back(d);
+      }
+      return;
+    }
+    d->ready_seen = true;
+  }
+  d->draining = false;
   arena_.release(d->off);
   d->dptr = nullptr;
   d->state = TFSC_STATE_END;
@@ -168,10 +184,22 @@ void Node::release_locked(const std::shared_ptr<DeviceModel>& d) {
     d->ready = nullptr;
   }
   ++ev_hbm_;
+  // END entries keep no DeviceModel (desc + op list): only the id survives, in a bounded FIFO, so GetModelStatus can
+  // still answer END for a recently unloaded servable
+  auto it = dev_.find(d->id);
+  if (it != dev_.end() && it->second == d) dev_.erase(it);
+  if (ended_.insert(d->id).second) {
+    ended_fifo_.push_back(d->id);
+    if (ended_fifo_.size() > 65536) {
+      ended_.erase(ended_fifo_.front());
+      ended_fifo_.pop_front();
+    }
+  }
   cv_.notify_all();
 }
 
-void Node::begin_unload_locked(const std::shared_ptr<DeviceModel>& d) {
+void Node::begin_unload_locked(const std::shared_ptr<DeviceModel>& d_in) {
+  const std::shared_ptr<DeviceModel> d = d_in;
   d->state = TFSC_STATE_UNLOADING;
   if (d->inflight == 0) release_locked(d);
 }
@@ -185,6 +213,18 @@ void Node::on_host_evict_locked(const CachedModel& m) {
 }
 
 void Node::reap_locked() {
+  for (size_t i = 0; i < drain_.size();) {  // blocks whose page-in was still in flight when they were unloaded
+    std::shared_ptr<DeviceModel> d = drain_[i];
+    if (cudaEventQuery(d->ready) != cudaSuccess) {
+      cudaGetLastError();
+      ++i;
+      continue;
+    }
+    d->ready_seen = true;
+    d->draining = false;
+    drain_.erase(drain_.begin() + i);
+    if (d->state == TFSC_STATE_UNLOADING && d->inflight == 0) release_locked(d);
+  }
   while (!retire_.empty()) {
     cudaError_t q = cudaEventQuery(retire_.front().ev);
     if (q != cudaSuccess) {
@@ -218,17 +258,21 @@ int Node::reload_locked(std::unique_lock<std::mutex>& lk, const ModelId& want, s
       if (m.id == want) want_in = true;
     }
     if (!want_in) {
+      CachedModel cm;
+      if (!lru_.peek(want, &cm)) return kRefetch;  // evicted from the host tier while mu_ was dropped: back to the miss path
       *err = "model " + want.name + ":" + std::to_string(want.version) + " does not fit the HBM arena (" +
              std::to_string(arena_.capacity()) + " bytes) / serving.maxConcurrentModels";
       return TFSC_E_EXHAUSTED;
     }
     // unload what fell out of the resident prefix (TF-Serving drops models absent from the new config)
+    std::vector<std::shared_ptr<DeviceModel>> drop;  // release_locked erases from dev_: collect first
     for (auto& kv : dev_) {
       auto& d = kv.second;
       if ((d->state == TFSC_STATE_AVAILABLE || d->state == TFSC_STATE_LOADING) &&
           !keep.count({d->id.name, d->id.version}))
-        begin_unload_locked(d);
+        drop.push_back(d);
     }
+    for (auto& d : drop) begin_unload_locked(d);
     // page in what is missing, MRU first
     for (auto& m : prefix) {
       auto it = dev_.find(m.id);
@@ -362,6 +406,7 @@ int Node::fetch(const ModelId& id, std::shared_ptr<DeviceModel>* pinned, std::st
     }
     if (outcome < 0) outcome = TFSC_FETCH_RELOAD;  // :133-143: cached but not resident
     int rc = reload_locked(lk, id, err);
+    if (rc == kRefetch) continue;
     if (rc < 0) {
       cache_dur_ += secs_since(t0);
       return rc;
@@ -397,6 +442,7 @@ int Node::status(const ModelId& id) {
   auto it = dev_.find(id);
   if (it == dev_.end()) {
     if (loading_.count(id)) return TFSC_STATE_START;
+    if (ended_.count(id)) return TFSC_STATE_END;
     return fail(TFSC_E_NOT_FOUND, "Model not found");  // servingcontroller.go:137
   }
   refresh_state_locked(it->second.get());

@@ -17,6 +17,7 @@
 #include <set>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "arena.h"
@@ -36,6 +37,7 @@ struct DeviceModel {
   cudaEvent_t ready = nullptr;  // recorded on the copy stream after the H2D page-in
   std::atomic<bool> ready_seen{false};  // event known complete: consumers skip the stream wait
   int inflight = 0;             // pins: launches that still read dptr
+  bool draining = false;        // unloaded while its page-in was still in flight: parked in Node::drain_
 };
 
 struct NodeConfig {
@@ -140,6 +142,10 @@ class Node {
   std::unordered_map<ModelId, std::shared_ptr<DeviceModel>, ModelIdHash> dev_;
   std::unordered_map<ModelId, int, ModelIdHash> loading_;  // provider loads in flight (1) / failed (-1)
   std::deque<Retire> retire_;
+  std::vector<std::shared_ptr<DeviceModel>> drain_;  // UNLOADING blocks waiting for their page-in event (never under a sync)
+  std::unordered_set<ModelId, ModelIdHash> ended_;   // ids of recently unloaded models (status END), bounded FIFO
+  std::deque<ModelId> ended_fifo_;
+  static constexpr int kRefetch = 1 << 20;           // reload_locked: model left the host tier meanwhile
   std::vector<cudaEvent_t> event_pool_;
 
   std::mutex scratch_mu_;

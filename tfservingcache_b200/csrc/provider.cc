@@ -65,8 +65,20 @@ static int64_t tree_size(const std::string& path) {
   return total;
 }
 
+// A model name is one path component below baseDir. The REST regex already forbids '/', the gRPC ModelSpec.name does
+// not, and the files found are parsed by native code in this process: refuse anything that could leave baseDir.
+static bool safe_model_name(const std::string& name, std::string* err) {
+  if (name.empty() || name == "." || name == ".." || name.find('/') != std::string::npos ||
+      name.find('\0') != std::string::npos) {
+    *err = "No matching model found";  // same answer as a model that does not exist (diskmodelprovider.go:67)
+    return false;
+  }
+  return true;
+}
+
 int64_t DiskModelProvider::model_size(const std::string& name, int64_t version, std::string* err) {
   std::string src;
+  if (!safe_model_name(name, err)) return -1;
   if (!find_src_path(base_dir_ + "/" + name, version, &src, err)) return -1;
   return tree_size(src);  // fix of diskmodelprovider.go:76-82 (dir inode size): real bytes
 }
@@ -90,6 +102,7 @@ static bool read_file(const std::string& path, std::string* out) {
 std::shared_ptr<HostModel> DiskModelProvider::load_model(const std::string& name, int64_t version,
                                                          const HostAllocFn& alloc, std::string* err) {
   std::string src;
+  if (!safe_model_name(name, err)) return nullptr;
   if (!find_src_path(base_dir_ + "/" + name, version, &src, err)) return nullptr;
   std::string mtxt;
   Json mj;
@@ -323,6 +336,7 @@ extern "C" {
 int tfsc_disk_find_version_dir(const char* base_dir, const char* model_name, int64_t version, char* buf, size_t cap) {
   if (!base_dir || !model_name) return tfsc::fail(TFSC_E_INVALID, "disk_find_version_dir: bad arguments");
   std::string out, err;
+  if (!tfsc::safe_model_name(model_name, &err)) return tfsc::fail(TFSC_E_NOT_FOUND, "%s", err.c_str());
   if (!tfsc::DiskModelProvider::find_src_path(std::string(base_dir) + "/" + model_name, version, &out, &err))
     return tfsc::fail(TFSC_E_NOT_FOUND, "%s", err.c_str());
   return tfsc::copy_out(out, buf, cap);

@@ -145,6 +145,10 @@ int ReplicaPicker::pick_ids(const std::string& key, const int* member_ids, int n
   int best = 0;
   for (int i = 1; i < n_replicas; ++i)
     if (load_[member_ids[i]] < load_[member_ids[best]]) best = i;
+  if (bound_.size() >= ((size_t)1 << 20)) {  // bounded memory: forget all bindings (deterministic for a given call sequence)
+    bound_.clear();
+    load_.clear();
+  }
   bound_[key] = member_ids[best];
   load_[member_ids[best]]++;
   return best;

@@ -9,6 +9,8 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 
 #include "json.h"
 #include "kernels.h"
@@ -65,9 +67,26 @@ static void set_members(tfsc_server* s, const std::vector<std::string>& members)
   for (size_t i = 0; i < s->local_members.size(); ++i) s->member_node[s->local_members[i]] = (int)i;
 }
 
+// No exception may cross the C ABI (a cgo / ctypes caller would see std::terminate): allocation failures and
+// anything else thrown below the entry points become error codes.
+template <typename F>
+static int guarded(const char* what, F&& f) {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    return fail(TFSC_E_EXHAUSTED, "%s: out of host memory", what);
+  } catch (const std::length_error&) {
+    return fail(TFSC_E_EXHAUSTED, "%s: request too large", what);
+  } catch (const std::exception& e) {
+    return fail(TFSC_E_INTERNAL, "%s: %s", what, e.what());
+  } catch (...) {
+    return fail(TFSC_E_INTERNAL, "%s: unknown exception", what);
+  }
+}
+
 extern "C" {
 
-tfsc_server* tfsc_server_create(const char* config_json) {
+static tfsc_server* server_create_impl(const char* config_json) {
   auto s = std::make_unique<tfsc_server>();
   std::string err;
   if (!config_json || !json_parse(config_json, &s->cfg, &err) || s->cfg.type != Json::Obj) {
@@ -261,17 +280,22 @@ static int resolve(tfsc_server* s, const std::string& name, const std::string& v
   return 0;
 }
 
-static void out_shape(const ModelDesc& d, int64_t rows, const std::vector<int64_t>& in_shape, std::vector<int64_t>* shape) {
+// Output shape of a request with input shape `in_shape` that the executor will run as `rows` rows. Returns false (with
+// a message) unless the shape accounts for exactly the rows * out_per_row elements the executor writes: the client's
+// tensor_shape must never be the only thing that sizes a response buffer (e.g. [1, 2*in_dim] is two rows, not one).
+static bool out_shape(const ModelDesc& d, int64_t rows, const std::vector<int64_t>& in_shape, std::vector<int64_t>* shape,
+                      std::string* why) {
+  shape->clear();
+  int64_t per_row = 1;
   if (d.tmpl == Template::Affine) {
     *shape = in_shape;
   } else if (d.tmpl == Template::Graph) {
     // [B, H, W, C] -> [B, classes]: batch dims are whatever precedes the per-image input shape
-    shape->clear();
     if (in_shape.size() > d.input_shape.size())
       for (size_t i = 0; i + d.input_shape.size() < in_shape.size(); ++i) shape->push_back(in_shape[i]);
     for (auto v : d.output_shape) shape->push_back(v);
+    per_row = d.out_dim;
   } else {
-    shape->clear();
     // leading dims of the input are kept ([B, in] -> [B, out]; [in] -> [out])
     if (in_shape.size() <= 1) {
       if (rows != 1 || in_shape.empty()) shape->push_back(rows);
@@ -279,11 +303,28 @@ static void out_shape(const ModelDesc& d, int64_t rows, const std::vector<int64_
       for (size_t i = 0; i + 1 < in_shape.size(); ++i) shape->push_back(in_shape[i]);
     }
     shape->push_back(d.out_dim);
+    per_row = d.out_dim;
   }
+  int64_t on = 1;
+  for (auto v : *shape) {
+    if (v < 0 || (v != 0 && on > ((int64_t)1 << 40) / v)) {
+      on = -1;
+      break;
+    }
+    on *= v;
+  }
+  if (on != rows * per_row) {
+    std::string sh = "[";
+    for (size_t i = 0; i < in_shape.size(); ++i) sh += (i ? "," : "") + std::to_string(in_shape[i]);
+    *why = "input shape " + sh + "] does not match the model signature: the trailing dimensions must hold exactly " +
+           std::to_string(d.tmpl == Template::Affine ? 1 : d.in_dim) + " elements per row";
+    return false;
+  }
+  return true;
 }
 
-int tfsc_predict(tfsc_server* s, const char* model_name, const char* version, const tfsc_tensor* in, int n_in,
-                 tfsc_tensor* out, int n_out) {
+static int predict_impl(tfsc_server* s, const char* model_name, const char* version, const tfsc_tensor* in, int n_in,
+                        tfsc_tensor* out, int n_out) {
   if (!s || !model_name || !version || !in || n_in < 1 || !out || n_out < 1)
     return fail(TFSC_E_INVALID, "predict: bad arguments");
   Node* node;
@@ -291,21 +332,25 @@ int tfsc_predict(tfsc_server* s, const char* model_name, const char* version, co
   int rc = resolve(s, model_name, version, &node, &id);
   if (rc < 0) return rc;
   const tfsc_tensor& x = in[0];
+  if (n_in != 1) return fail(TFSC_E_INVALID, "predict: the model templates take exactly one input tensor (got %d)", n_in);
   if ((x.dtype != TFSC_DT_FLOAT && x.dtype != TFSC_DT_INT32) || x.rank < 0 || x.rank > 8)
     return fail(TFSC_E_INVALID, "predict: input must be DT_FLOAT or DT_INT32, rank <= 8");
   int64_t n = 1;
   std::vector<int64_t> ishape(x.shape, x.shape + x.rank);
-  for (auto d : ishape) n *= d;
+  for (auto d : ishape) {
+    if (d < 0 || (d != 0 && n > ((int64_t)1 << 40) / d)) return fail(TFSC_E_INVALID, "predict: bad input shape");
+    n *= d;
+  }
   if ((size_t)n * 4 != x.nbytes) return fail(TFSC_E_INVALID, "predict: input nbytes does not match shape");
-  std::string err;
+  std::string err, bad;
   tfsc_tensor* o = &out[0];
   auto alloc = [&](const ModelDesc& d, int64_t rows) -> void* {
-    if (n_in > 1 || (x.name && d.input_name != x.name)) {
-      // signature check: the template has exactly one input
-      if (x.name && d.input_name != x.name) return nullptr;
+    if (x.name && d.input_name != x.name) {  // signature check: the template has exactly one input
+      bad = "input '" + std::string(x.name) + "' does not match the model signature (expects '" + d.input_name + "')";
+      return nullptr;
     }
     std::vector<int64_t> sh;
-    out_shape(d, rows, ishape, &sh);
+    if (!out_shape(d, rows, ishape, &sh, &bad)) return nullptr;
     int64_t on = 1;
     for (auto v : sh) on *= v;
     if (!o->data || o->nbytes < (size_t)on * 4 || sh.size() > 8) return nullptr;
@@ -316,11 +361,12 @@ int tfsc_predict(tfsc_server* s, const char* model_name, const char* version, co
     return o->data;
   };
   rc = node->predict_host(id, x.data, n, x.dtype, alloc, nullptr, nullptr, &err);
+  if (rc < 0 && !bad.empty()) return fail(TFSC_E_INVALID, "%s", bad.c_str());
   if (rc < 0) return fail(rc, "%s", err.c_str());
   return 0;
 }
 
-int tfsc_grpc_predict(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len) {
+static int grpc_predict_impl(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len) {
   if (!s || !req || !resp || !resp_len) return fail(TFSC_E_INVALID, "grpc_predict: bad arguments");
   s->req_grpc++;  // promRequestsTotal{grpc}, tfservingproxy.go:202
   PredictRequestView view;
@@ -369,7 +415,7 @@ int tfsc_grpc_predict(tfsc_server* s, const void* req, size_t req_len, void** re
       return nullptr;
     }
     std::vector<int64_t> sh;
-    out_shape(d, rows, tv.shape, &sh);
+    if (!out_shape(d, rows, tv.shape, &sh, &bad_sig)) return nullptr;
     std::string prefix, suffix;
     predict_response_frame(view.model_name, id.version, view.signature_name.empty() ? "serving_default" : view.signature_name,
                            d.output_name, sh, &prefix, &suffix);
@@ -476,8 +522,8 @@ static void write_tensor_json(const float* v, const std::vector<int64_t>& shape,
   *s += "]";
 }
 
-int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const void* body, size_t body_len,
-                     int* http_status, void** resp, size_t* resp_len) {
+static int rest_handle_impl(tfsc_server* s, const char* method, const char* url, const void* body, size_t body_len,
+                            int* http_status, void** resp, size_t* resp_len) {
   if (!s || !method || !url || !http_status || !resp || !resp_len) return fail(TFSC_E_INVALID, "rest_handle: bad arguments");
   s->req_rest++;  // promRequestsTotal{rest}, tfservingproxy.go:96
   std::string name, version;
@@ -573,7 +619,7 @@ int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const 
         bad_sig = "input '" + input_key + "' does not match the model signature (expects '" + d.input_name + "')";
         return nullptr;
       }
-      out_shape(d, rows, shape, &oshape);
+      if (!out_shape(d, rows, shape, &oshape, &bad_sig)) return nullptr;
       int64_t on = 1;
       for (auto v : oshape) on *= v;
       y.resize((size_t)on);
@@ -632,6 +678,26 @@ int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const 
     return fail_http(400, "Expected classification/regression signature; model " + name + " exports a predict signature only");
   }
   return fail_http(400, "Malformed request: " + m + " " + u);
+}
+
+tfsc_server* tfsc_server_create(const char* config_json) {
+  tfsc_server* out = nullptr;
+  guarded("server_create", [&] {
+    out = server_create_impl(config_json);
+    return 0;
+  });
+  return out;
+}
+int tfsc_predict(tfsc_server* s, const char* model_name, const char* version, const tfsc_tensor* in, int n_in,
+                 tfsc_tensor* out, int n_out) {
+  return guarded("predict", [&] { return predict_impl(s, model_name, version, in, n_in, out, n_out); });
+}
+int tfsc_grpc_predict(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len) {
+  return guarded("grpc_predict", [&] { return grpc_predict_impl(s, req, req_len, resp, resp_len); });
+}
+int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const void* body, size_t body_len,
+                     int* http_status, void** resp, size_t* resp_len) {
+  return guarded("rest_handle", [&] { return rest_handle_impl(s, method, url, body, body_len, http_status, resp, resp_len); });
 }
 
 int tfsc_predict_device(tfsc_server* s, int node, const char* model_name, int64_t version, const void* x,

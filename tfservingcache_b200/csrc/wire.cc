@@ -152,6 +152,9 @@ bool decode_predict_request(const void* data, size_t len, PredictRequestView* ou
   return true;
 }
 
+// 16 Mi elements = 64 MB = 4x the reference's 16 MiB gRPC message limit (cachemanager.go:230-233)
+static constexpr int64_t kMaxBroadcastElements = (int64_t)16 << 20;
+
 bool tensor_f32(const TensorView& t, const float** data, int64_t* n, std::vector<float>* scratch, std::string* err) {
   if (t.dtype != TFSC_DT_FLOAT) {
     *err = "input '" + t.name + "' has dtype " + std::to_string(t.dtype) + "; only DT_FLOAT (1) is supported";
@@ -163,6 +166,10 @@ bool tensor_f32(const TensorView& t, const float** data, int64_t* n, std::vector
       return false;
     }
   const int64_t want = t.num_elements();
+  if (want < 0) {
+    *err = "input '" + t.name + "': tensor_shape is too large";
+    return false;
+  }
   if (t.content_len) {
     if ((int64_t)(t.content_len / 4) != want || t.content_len % 4) {
       *err = "tensor_content size does not match tensor_shape";
@@ -196,6 +203,11 @@ bool tensor_f32(const TensorView& t, const float** data, int64_t* n, std::vector
     return true;
   }
   if (have == 1 && want > 1) {  // TF semantics: a single value fills the tensor
+    if (want > kMaxBroadcastElements) {  // the only path where a few request bytes size a large allocation
+      *err = "input '" + t.name + "': scalar broadcast to " + std::to_string(want) + " elements exceeds the limit of " +
+             std::to_string(kMaxBroadcastElements);
+      return false;
+    }
     float fv;
     memcpy(&fv, src, 4);
     scratch->assign(want, fv);
@@ -218,6 +230,10 @@ bool tensor_i32(const TensorView& t, const int32_t** data, int64_t* n, std::vect
       return false;
     }
   const int64_t want = t.num_elements();
+  if (want < 0) {
+    *err = "input '" + t.name + "': tensor_shape is too large";
+    return false;
+  }
   if (t.content_len) {
     if ((int64_t)(t.content_len / 4) != want || t.content_len % 4) {
       *err = "tensor_content size does not match tensor_shape";
@@ -228,6 +244,11 @@ bool tensor_i32(const TensorView& t, const int32_t** data, int64_t* n, std::vect
   } else if ((int64_t)t.ints.size() == want) {
     *scratch = t.ints;
   } else if (t.ints.size() == 1 && want > 1) {
+    if (want > kMaxBroadcastElements) {
+      *err = "input '" + t.name + "': scalar broadcast to " + std::to_string(want) + " elements exceeds the limit of " +
+             std::to_string(kMaxBroadcastElements);
+      return false;
+    }
     scratch->assign(want, t.ints[0]);
   } else {
     *err = "int_val count " + std::to_string(t.ints.size()) + " does not match tensor_shape (" + std::to_string(want) + ")";

@@ -21,9 +21,16 @@ struct TensorView {
   size_t packed_f32_len = 0;
   std::vector<float> loose_f32;  // unpacked float_val entries
   std::vector<int32_t> ints;     // int_val entries (packed or not), field 7
+  // product of the dims, or -1 if a dim is negative or the product overflows / exceeds kMaxTensorElements
+  // (a client-controlled shape must never size an allocation unchecked)
+  static constexpr int64_t kMaxTensorElements = (int64_t)1 << 31;
   int64_t num_elements() const {
     int64_t n = 1;
-    for (auto d : shape) n *= d;
+    for (auto d : shape) {
+      if (d < 0) return -1;
+      if (d != 0 && n > kMaxTensorElements / d) return -1;
+      n *= d;
+    }
     return n;
   }
 };
