@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--workload", default="mlp", choices=["mlp", "resnet50"],
                     help="mlp = BASELINE configs[2] shard (default, the headline); resnet50 = configs[1] (100 ResNet-50 per GPU, "
                          "32 HBM-resident, LRU paging in the loop) -- an extra line")
+    ap.add_argument("--preheat-s", type=float, default=2.0, help="untimed seconds of real passes right before the timed region")
+    ap.add_argument("--samplers", default="smi+nvml", choices=["smi+nvml", "smi", "nvml", "none"],
+                    help="clock samplers running during the timed regions (A/B their perturbation with 'none')")
     ap.add_argument("--replica-pick", default="balanced", choices=["balanced", "hot-spread", "random", "first"],
                     help="replica choice among the ring's GetN candidates (reference: random)")
     return ap.parse_args()
@@ -93,7 +96,7 @@ def splitmix(i: np.ndarray) -> np.ndarray:
 def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42, pick_policy="balanced"):
     """Global request stream + ring routing, identical on every rank (no communication)."""
     import tfservingcache_b200 as t
-    from oracle.zipf import zipf_trace  # trace generator only (test/bench infrastructure)
+    from tools.traces import zipf_trace
     n_models = models_per_gpu * n_gpus
     replicas = min(2, n_gpus)
     members = [f"gpu{i}:0:0" for i in range(n_gpus)]
@@ -381,11 +384,20 @@ def run_b200(args):
     for s in range(W):
         device_step(s)
     barrier()
+    # pre-heat: the W warm-up steps follow ~45 s of cold loads with an idle GPU; run real passes for --preheat-s more so
+    # clocks, power state and the driver's launch path are in steady state when the clock starts (r1: N=1 varied 36-48 k)
+    t_heat, i_heat = time.time(), 0
+    while time.time() - t_heat < args.preheat_s:
+        device_step(i_heat % max(W, 1))
+        torch.cuda.synchronize()
+        i_heat += 1
+    barrier()
     flush.fill_(1)  # inputs (>= 1 GB of weights per launch) already exceed L2; flush once anyway
-    sampler = ClockSampler(local, enabled=(local == 0))
+    sampler = ClockSampler(local, enabled=(local == 0 and "smi" in args.samplers))
     sampler.start()
-    nvml = NvmlSampler(local, period_s=0.02 if world == 1 else 0.1)   # every rank watches its own GPU
-    nvml.start()
+    nvml = NvmlSampler(local, period_s=0.1)   # every rank watches its own GPU
+    if "nvml" in args.samplers:
+        nvml.start()
     launches0 = _lib.lib.tfsc_kernel_launches()
     st0 = srv.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -557,7 +569,7 @@ def cpu_reference(n_sample, dims, warm=4, steps=None):
     from oracle import models as omodels
     from oracle import ring as oring
     from oracle.lrucache import Model, ModelIdentifier
-    from oracle.zipf import zipf_trace
+    from tools.traces import zipf_trace
 
     cores = min(effective_cpus(), 256)
     liborc = C.CDLL(os.path.join(ROOT, "oracle", "liboracle_ref.so"))
@@ -656,6 +668,8 @@ def run_reference(args):
 
 
 if __name__ == "__main__":
+    import faulthandler
+    faulthandler.enable()   # a native crash prints the Python stack it happened under
     a = parse_args()
     try:
         if a.impl == "reference":

@@ -219,10 +219,12 @@ int tfsc_k_affine(const float* x, float* y, int64_t n, const float* a, const flo
 int tfsc_k_dense(const float* x, const float* w, const float* b, float* y, int rows, int k, int n, int relu,
                  float* workspace, size_t workspace_bytes, void* stream);                                    /* X2 */
 size_t tfsc_k_dense_workspace(int rows, int k, int n);
-/* tfsc_k_dense with an explicit kernel choice: 0 auto, 1 LDG-stream SIMT only, 2 / 4 bulk-copy (TMA) ring with 8 / 4
- * k-lanes for the <= 8-row passes, 3 tensor cores for every row count, 5 cluster-pair kernel (two CTAs split K and meet in
- * distributed shared memory; EXPERIMENTAL, see csrc/dense_cluster.cu). Same arguments, workspace and results (the fp32
- * summation order differs between variants; each variant is bit-reproducible). */
+/* tfsc_k_dense with an explicit kernel choice: 0 auto (<= 8 rows: cluster-pair kernel with programmatic dependent launch,
+ * csrc/dense_cluster.cu -- two CTAs split K and meet in distributed shared memory; more rows: tensor cores), 1 LDG-stream
+ * SIMT kernel with split-K workspace (the round-1 default; still the fallback for shapes the cluster kernel does not take),
+ * 2 / 4 bulk-copy (TMA) ring with 8 / 4 k-lanes, 3 tensor cores for every row count, 5 cluster-pair kernel for <= 8 rows and
+ * the SIMT fallback otherwise. Same arguments, workspace and results (the fp32 summation order differs between variants; each
+ * variant is bit-reproducible). */
 int tfsc_k_dense_variant(int variant, const float* x, const float* w, const float* b, float* y, int rows, int k, int n,
                          int relu, float* workspace, size_t workspace_bytes, void* stream);
 /* X3: the tcgen05/TMEM (3xTF32) path alone, rows <= 64, n % 32 == 0, k % 4 == 0. tfsc_k_dense picks it

@@ -2,7 +2,8 @@
 N back-to-back launches / N (per-launch event pairs are quantised to ~2 us on these boxes and hide small differences).
 Three weight buffers rotate so no launch finds its W in L2. PDL is a process-level switch:
     for p in 0 1; do for v in 1 2 4; do TFSC_PDL=$p python profiles/time_dense_total.py $v; done; done
-Usage: python profiles/time_dense_total.py [variant=1] [launches=300]  -> one JSON line per row count"""
+Usage: python profiles/time_dense_total.py [variant=1] [launches=300] [rows=1,2,4,8]  -> one JSON line per row count
+(variant 3 = tensor-core path for every row count, e.g. rows 16,32,48,64)"""
 import json
 import os
 import sys
@@ -14,11 +15,12 @@ import tfservingcache_b200 as t  # noqa: E402
 
 variant = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 launches = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+row_list = tuple(int(v) for v in sys.argv[3].split(",")) if len(sys.argv) > 3 else (1, 2, 4, 8)
 K = N = 9216
 lib = t._lib.lib
 w3 = [torch.randn(K, N, device="cuda") / 96 for _ in range(3)]
 b = torch.randn(N, device="cuda")
-for rows in (1, 2, 4, 8):
+for rows in row_list:
     x = torch.randn(rows, K, device="cuda")
     y = torch.empty(rows, N, device="cuda")
     ws_bytes = lib.tfsc_k_dense_workspace(rows, K, N)

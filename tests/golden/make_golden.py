@@ -193,7 +193,7 @@ def ring_golden():
 def trace_golden():
     from oracle import cachemanager as ocm
     from oracle.lrucache import Model, ModelIdentifier
-    from oracle.zipf import zipf_trace
+    from tools.traces import zipf_trace
 
     class Prov:
         def __init__(self, sizes):

@@ -170,11 +170,11 @@ def test_request_shape_cannot_undersize_the_response(endpoints):
     two_rows_as_one = np.random.default_rng(5).standard_normal((1, 2 * DIMS[0])).astype(np.float32)
     st, body = _http(f"{base}/v1/models/m3/versions/1:predict", json.dumps({"instances": two_rows_as_one.tolist()}).encode())
     assert st == 400 and b"does not match the model signature" in body
-    with pytest.raises(t.TfscError) as e:
+    with pytest.raises(t._lib.TfscError) as e:
         srv.grpc_predict(wire.encode_predict_request("m3", 1, {"x": two_rows_as_one}))
     assert e.value.code == t._lib.E_INVALID
     # C ABI with an output buffer sized from the (wrong) shape the client claims: must fail, not overflow
-    with pytest.raises(t.TfscError) as e:
+    with pytest.raises(t._lib.TfscError) as e:
         srv.predict("m3", "1", two_rows_as_one, out_capacity_elems=DIMS[-1])
     assert e.value.code == t._lib.E_INVALID
     # a flat vector of 2*in_dim elements is two rows: accepted, shape [2, out]
@@ -206,7 +206,7 @@ def test_scalar_broadcast_is_bounded(endpoints):
         return b"\x0a" + _varint(len(spec)) + spec + b"\x12" + _varint(len(entry)) + entry
 
     for dim in (1 << 33, 1 << 62, (1 << 24) + 1):
-        with pytest.raises(t.TfscError) as e:
+        with pytest.raises(t._lib.TfscError) as e:
             srv.grpc_predict(req(dim))
         assert e.value.code == t._lib.E_INVALID
     # the legitimate use still works: one value fills a [2, in] tensor

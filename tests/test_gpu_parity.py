@@ -14,7 +14,7 @@ from oracle import cachemanager as ocm
 from oracle import models, wire
 from oracle.lrucache import Model as OModel
 from oracle.lrucache import ModelIdentifier as OId
-from oracle.zipf import zipf_trace
+from tools.traces import zipf_trace
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4  # north_star: fp32 outputs within 1e-4

@@ -319,7 +319,7 @@ def test_replica_picker_policies():
     assert 800 < c[0] < 1200 and set(c) == {0, 1}
     # same seed + same call sequence -> same decisions (ranks agree without communicating)
     a, b = t.ReplicaPicker("hot-spread", 42), t.ReplicaPicker("hot-spread", 42)
-    from oracle.zipf import zipf_trace
+    from tools.traces import zipf_trace
     tr = zipf_trace(1000, 30000, 1.0, 42).tolist()
     pa = [a.pick(f"m{m}##1", 2, 8) for m in tr]
     assert pa == [b.pick(f"m{m}##1", 2, 8) for m in tr]

@@ -1,5 +1,6 @@
-// X2, cluster-pair variant of the fused dense pass (tfsc_k_dense_variant 5; EXPERIMENTAL: written after the round's GPU
-// budget was spent, compiled for sm_100a but not yet run -- never selected automatically):
+// X2, cluster-pair kernel of the fused dense pass: the DEFAULT for <= 8 rows per pass since round 2 (tfsc_k_dense_variant 0 / 5).
+// Measured on B200 (profiles/r2/dense_ab.jsonl, 300 back-to-back launches of one 9216x9216 layer, cold L2): 51.8 us at 8 rows,
+// 49.1 us at 1 row with programmatic dependent launch (55.5 / 53.2 us without) vs 61.1 / 54.1 us for dense_stream_kernel.
 //
 //   y[R,N] = act(x[R,K] W[K,N] + b),  R <= 8 rows per pass, fp32.
 //
@@ -200,6 +201,9 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap wmap, const float* __re
 
   // ---- k-lane reduction through shared memory (the ring is idle: every full barrier was waited on) ----
   __syncthreads();
+  // every thread that is about to write y observes the completion of the prerequisite grid itself (y may be a buffer
+  // the previous kernel of the stream still read); long satisfied by now, no-op without the PDL launch attribute
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   float* red = reinterpret_cast<float*>(ring);                     // [KLANES][R][STRIP]   (64 KB at R = 8)
   float* res = red + cl::KLANES * R * cl::STRIP;                   // [R][STRIP]           (4 KB at R = 8)
   if (warp < cl::KLANES) {
@@ -290,9 +294,9 @@ static cudaError_t launch_cl_r(const CUtensorMap& map, const float* x, const flo
     if (e != cudaSuccess) return e;
     attr[dev & 63] = true;
   }
-  static const bool pdl = [] {
+  static const bool pdl = [] {  // programmatic dependent launch is on unless TFSC_PDL=0
     const char* e = getenv("TFSC_PDL");
-    return e && atoi(e) != 0;
+    return !e || atoi(e) != 0;
   }();
   const int strips = (n + cl::STRIP - 1) / cl::STRIP;
   int k_half = ((k + 1) / 2 + cl::SK - 1) / cl::SK * cl::SK;   // rank 0 takes [0, k_half), rank 1 the rest

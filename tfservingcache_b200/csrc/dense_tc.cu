@@ -15,11 +15,16 @@
 //     MMA2 D[:, R:2R] += W_lo . x_hi^T (N = R); accumulators live in TMEM; y = D[:, :R] + D[:, R:2R]: the large
 //     term and the small correction terms are kept apart because the tensor core's fp32 accumulation truncates.
 //   * split-K over CTAs (one CTA per SM), partials folded by the last CTA of a strip in fixed order
-//     (same deterministic scheme as dense_stream_kernel), bias + ReLU fused there.
+//     (same deterministic scheme as dense_stream_kernel), bias + ReLU fused there. (A thread-block cluster per strip
+//     with a DSMEM fold, as in dense_cluster.cu, does not fit: 36 strips x 4 K-splits would need 36 clusters of 4 and
+//     B200 co-schedules at most 33 of them -- 132 of 148 SMs -- so the grid would take a second wave.)
+//   * programmatic dependent launch (round 2): the W ring fills (TMA) under the previous kernel's tail; x, the
+//     split-K workspace and y are touched only after griddepcontrol.wait.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -113,6 +118,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap wmap, const float* __restric
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // no-op without the PDL launch attribute
 
   if (warp == 0) {
     // ===================== TMA producer: keeps NS x 32 KB of W in flight =====================
@@ -190,6 +196,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap wmap, const float* __restric
         dst[j] = v;
       }
     };
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // x is the previous kernel's output; W (TMA warp) never is
     if (n_kblocks > 0) load_x(0, xr[0]);
     if (n_kblocks > 1) load_x(1, xr[1]);
     // shared address of this thread's column inside a W stage, before the per-row swizzle
@@ -262,6 +269,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap wmap, const float* __restric
 
   // ---- teardown + deterministic split-K fold by the last CTA of the strip ----
   __shared__ unsigned int s_last;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // workspace counters / y: every thread observes the prerequisite grid
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __threadfence();
   __syncthreads();
@@ -390,11 +398,24 @@ static cudaError_t launch_tc_rp(const CUtensorMap& map, const float* x, const fl
   unsigned int* counters = static_cast<unsigned int*>(workspace);
   size_t coff = ((size_t)p.strips * sizeof(unsigned int) + 255) & ~(size_t)255;
   float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + coff);
-  dim3 grid(p.strips, p.splits);
-  dense_tc_kernel<RP><<<grid, tc::THREADS, TcSmem<RP>::TOTAL, s>>>(map, x, bias, y, rows, k, n, relu ? 1 : 0, p.splits,
-                                                                   p.chunk_k, counters, partials);
+  static const bool pdl = [] {  // programmatic dependent launch is on unless TFSC_PDL=0
+    const char* e = getenv("TFSC_PDL");
+    return !e || atoi(e) != 0;
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.strips, p.splits);
+  cfg.blockDim = dim3(tc::THREADS);
+  cfg.dynamicSmemBytes = TcSmem<RP>::TOTAL;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, dense_tc_kernel<RP>, map, x, bias, y, rows, k, n, relu ? 1 : 0, p.splits, p.chunk_k, counters,
+                                     partials);
   g_launches_tc++;
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_dense_tc(const float* x, const float* w, const float* bias, float* y, int rows, int k, int n, bool relu,

@@ -631,7 +631,9 @@ cudaError_t launch_dense(const float* x, const float* w, const float* bias, floa
     const float* xp = x + (size_t)r0 * k;
     float* yp = y + (size_t)r0 * n;
     cudaError_t e;
-    if (variant == 5 && dense_cluster_supported(rr, k, n, w, xp, bias, yp)) {
+    // default for <= 8 rows: the cluster-pair kernel with programmatic dependent launch (measured round 2: 51.8 us per
+    // 9216x9216 layer at 8 rows = the measured HBM copy peak, vs 61.1 us for the LDG stream kernel with its split-K tail)
+    if ((variant == 0 || variant == 5) && dense_cluster_supported(rr, k, n, w, xp, bias, yp)) {
       e = launch_dense_cluster(xp, w, bias, yp, rr, k, n, relu, s);
       if (e != cudaSuccess) return e;
       continue;

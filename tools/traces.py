@@ -1,5 +1,5 @@
 """Seeded Zipf(alpha) multi-model request trace: p(rank r) = 1/(r^a H_N),
-rank -> model id through a seeded permutation.  Test/bench infrastructure."""
+rank -> model id through a seeded permutation.  Workload generator for bench.py and the tests (not part of the oracle: the product arm of bench.py must not import oracle/)."""
 from __future__ import annotations
 
 import numpy as np
