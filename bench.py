@@ -11,9 +11,15 @@ A "step" is one batcher tick: `--tick` (default 1024) requests per GPU drawn fro
 trace, routed with the consistent-hash ring, grouped per resident model and executed.
   value  : whole-job req/s with the step's inputs already resident in HBM (device pointers through
            tfsc_predict_device), timed with CUDA events on the launching stream.
-  e2e    : the same ticks through the public C ABI call tfsc_predict() with HOST buffers from
-           `--clients` closed-loop client threads (H2D of inputs + D2H of results inside the timed
-           region), plus p50/p99 latency.
+  e2e    : the same ticks through the public C ABI (tfsc_predict / tfsc_predict_member) with HOST buffers from
+           `--clients` closed-loop client threads (transfers of inputs and results inside the timed
+           region), plus p50/p99 latency and a client sweep for the QPS that still meets p50 < 5 ms.
+  forward: at N > 1 a fraction `--forward-frac` of the requests ENTERS at a rank that does not own the model
+           (a6, taskhandler.go:95-147): their rows sit in the ingress rank's forward window and the owner reads /
+           writes them over NVLink (gather / scatter kernels), in both the value and the e2e region.
+  cache_pressure: a short phase with the HBM-resident set capped below the working set (uniform trace, BASELINE
+           configs[4]-style storm): hit %, reloads, H2D GB/s against the PCIe roofline, load-stall p99.
+  extra  : device-resident ResNet-50 (configs[1]) and BERT-base (configs[3]) model speed, N=1 only.
   --impl reference : the reference's CPU path restated (ring -> LRU/top-N residency -> per-request,
            unbatched fp32 forward on all host cores, oracle C), on a bounded sample.
 """
@@ -56,13 +62,14 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident part alone")
     ap.add_argument("--light-clients", type=int, default=16, help="clients per GPU of the light-load latency probe (0 = skip)")
     ap.add_argument("--dims", type=int, nargs="*", default=None, help="override model dims (debug only)")
-    ap.add_argument("--workload", default="mlp", choices=["mlp", "resnet50"],
-                    help="mlp = BASELINE configs[2] shard (default, the headline); resnet50 = configs[1] (100 ResNet-50 per GPU, "
-                         "32 HBM-resident, LRU paging in the loop) -- an extra line")
+    ap.add_argument("--forward-frac", type=float, default=0.25,
+                    help="N > 1: fraction of requests whose ingress rank is not the owner (forward hop over NVLink)")
+    ap.add_argument("--no-extras", action="store_true", help="skip cache_pressure / sweep / extra model lines (profiling runs)")
+    ap.add_argument("--pressure-resident", type=int, default=32, help="HBM-resident cap of the cache_pressure phase")
     ap.add_argument("--preheat-s", type=float, default=2.0, help="untimed seconds of real passes right before the timed region")
     ap.add_argument("--samplers", default="smi+nvml", choices=["smi+nvml", "smi", "nvml", "none"],
                     help="clock samplers running during the timed regions (A/B their perturbation with 'none')")
-    ap.add_argument("--replica-pick", default="balanced", choices=["balanced", "hot-spread", "random", "first"],
+    ap.add_argument("--replica-pick", default="balanced", choices=["balanced", "hot-spread", "random", "first", "hash"],
                     help="replica choice among the ring's GetN candidates (reference: random)")
     return ap.parse_args()
 
@@ -93,7 +100,7 @@ def splitmix(i: np.ndarray) -> np.ndarray:
     return z ^ (z >> np.uint64(31))
 
 
-def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42, pick_policy="balanced"):
+def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42, pick_policy="balanced", forward_frac=0.0):
     """Global request stream + ring routing, identical on every rank (no communication)."""
     import tfservingcache_b200 as t
     from tools.traces import zipf_trace
@@ -115,8 +122,16 @@ def build_workload(n_gpus, models_per_gpu, tick, n_steps, seed=42, pick_policy="
     own = [[int(v) for v in owners[j]] for j in range(n_models)]
     pick = np.fromiter((picker.pick_ids(keys[m], own[m], n_gpus) for m in trace.tolist()), dtype=np.int64, count=total)
     dest = owners[trace, pick]
+    # ingress rank of every request: the owner itself, or (fraction forward_frac) another rank chosen uniformly -- the
+    # front load balancer of a real deployment does not know the ring
+    ingress = dest.copy()
+    if n_gpus > 1 and forward_frac > 0:
+        rng = np.random.default_rng(seed + 7)
+        fw = rng.random(total) < forward_frac
+        other = (dest + rng.integers(1, n_gpus, size=total)) % n_gpus
+        ingress = np.where(fw, other, dest).astype(dest.dtype)
     return dict(n_models=n_models, replicas=replicas, members=members, trace=trace, dest=dest, owners=owners,
-                pick_policy=pick_policy)
+                pick_policy=pick_policy, ingress=ingress, forward_frac=forward_frac if n_gpus > 1 else 0.0)
 
 
 def step_groups(wl, rank, step, tick_global):
@@ -130,6 +145,30 @@ def step_groups(wl, rank, step, tick_global):
             counts[m] = 0
         counts[m] += 1
     return mine, [(m, counts[m]) for m in order]
+
+
+def step_plan(wl, rank, step, tick_global):
+    """Owner-side plan of one step: for every model group owned by `rank`, how many rows entered locally and, for the
+    forwarded rows, (ingress rank, slot index k in that rank's forward window). k enumerates ALL forwarded requests of
+    the ingress rank in the step, so owners writing results into the same window never collide."""
+    lo, hi = step * tick_global, (step + 1) * tick_global
+    tr, de, ing = wl["trace"][lo:hi], wl["dest"][lo:hi], wl["ingress"][lo:hi]
+    fw = ing != de
+    slot_k = np.zeros(hi - lo, np.int64)
+    for p in np.unique(ing[fw]).tolist():
+        sel = np.nonzero(fw & (ing == p))[0]
+        slot_k[sel] = np.arange(len(sel))
+    order, local, fwd = [], {}, {}
+    for i in np.nonzero(de == rank)[0].tolist():
+        m = int(tr[i])
+        if m not in local:
+            order.append(m)
+            local[m], fwd[m] = 0, []
+        if fw[i]:
+            fwd[m].append((int(ing[i]), int(slot_k[i])))
+        else:
+            local[m] += 1
+    return [(m, local[m], fwd[m]) for m in order]
 
 
 def pass_plan(rows, tc_min=9):
@@ -276,6 +315,58 @@ class NvmlSampler:
 
 
 # ------------------------------------------------------------------------------- b200 impl ------
+def workload_string(models_per_gpu, dims, replicas, pick_policy):
+    """config.workload, identical for the b200 arm and the reference arm (same workload, two implementations)"""
+    model_bytes = sum(dims[i] * dims[i + 1] * 4 + dims[i + 1] * 4 for i in range(len(dims) - 1))
+    return (f"BASELINE configs[2] per-GPU shard: {models_per_gpu} per-tenant 3-layer MLP "
+            f"({'x'.join(map(str, dims))} fp32, {model_bytes} B) per GPU, Zipf alpha=1.0, ring replicas={replicas} "
+            f"(replica pick: {pick_policy}); at 8 GPUs = configs[2] (1000 models)")
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
+def graph_model_speed(kind, steps=30):
+    """extra.<kind>: device-resident speed of one BASELINE configs[1] / configs[3] model (synthetic weights, batch 8):
+    tfsc_predict_device in a loop, CUDA events. Returns a small dict for the bench line."""
+    import torch
+    import tfservingcache_b200 as t
+    if kind == "resnet50":
+        man = t.modelformat.resnet50_manifest()
+        rows, in_elems, out_elems, flop = 8, 224 * 224 * 3, 1000, 8.2e9
+        x = torch.rand(rows, in_elems, device="cuda")
+    else:
+        man = t.modelformat.bert_manifest()
+        rows, in_elems, out_elems, flop = 8, 128, 2, 22.4e9   # ~180 GFLOP per 8 x 128 request
+        x = torch.randint(1, 30522, (rows, in_elems), device="cuda", dtype=torch.int32)
+    y = torch.empty(rows, out_elems, device="cuda")
+    cfg = {"modelProvider.type": "synthetic", "modelProvider.synthetic.template": "manifest",
+           "modelProvider.synthetic.manifest": man, "modelProvider.synthetic.count": 2, "gpu.devices": [torch.cuda.current_device()],
+           "gpu.arenaBytes": 2 << 30, "serving.maxConcurrentModels": 2, "modelCache.size": 4 << 30, "gpu.maxBatch": 8}
+    stream = torch.cuda.Stream()
+    with t.Server(cfg) as srv, torch.cuda.stream(stream):
+        srv.ensure(0, "m0", 1)
+        l0 = t._lib.lib.tfsc_kernel_launches()
+        for _ in range(3):
+            srv.predict_device(0, "m0", 1, x.data_ptr(), rows, y.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        per_pass = (t._lib.lib.tfsc_kernel_launches() - l0) // 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            srv.predict_device(0, "m0", 1, x.data_ptr(), rows, y.data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    tfl = flop * rows / (ms * 1e-3) / 1e12
+    peak = _peaks().get("bf16_tflops_sustained", 1405.4)
+    return {"batch": rows, "ms_per_batch": round(ms, 3), "items_per_s": round(rows / (ms * 1e-3), 1), "tflops": round(tfl, 2),
+            "frac_of_bf16_sustained": round(tfl / peak, 4), "launches_per_batch": int(per_pass), "weights_bytes": man["weights_bytes"],
+            "note": "fp32 in/out, 3xTF32 tcgen05 GEMMs; device-resident inputs, one model, CUDA events"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -295,46 +386,43 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dims = args.dims or DIMS
     in_dim, out_dim = dims[0], dims[-1]
+    inb, outb = in_dim * 4, out_dim * 4
     model_bytes = sum(dims[i] * dims[i + 1] * 4 + dims[i + 1] * 4 for i in range(len(dims) - 1))
-    graph_man = None
-    if args.workload == "resnet50":
-        graph_man = t.modelformat.resnet50_manifest()
-        in_dim, out_dim, model_bytes = 224 * 224 * 3, 1000, graph_man["weights_bytes"]
-        if args.models_per_gpu == MODELS_PER_GPU:
-            args.models_per_gpu = 100
-        if args.tick == 1024:
-            args.tick = 24      # distinct models per tick stay below the 32-model HBM cache (a tick is executed as one batch wave)
-        args.clients = min(args.clients, 64)
     W, K = args.warmup, args.steps
     e2e_steps = args.e2e_steps or K
     n_steps_total = W + K + W + e2e_steps
-    wl = build_workload(world, args.models_per_gpu, args.tick, n_steps_total, pick_policy=args.replica_pick)
+    fwd_frac = args.forward_frac if world > 1 else 0.0
+    wl = build_workload(world, args.models_per_gpu, args.tick, n_steps_total, pick_policy=args.replica_pick, forward_frac=fwd_frac)
     tick_global = args.tick * world
 
     free_b, _tot = torch.cuda.mem_get_info()
     arena = min(int(args.arena_gib * 2**30), int(free_b * 0.9))
     my_models = sorted({int(m) for m in np.unique(wl["trace"][wl["dest"] == rank])})
     host_gib = args.host_gib
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
     if host_gib <= 0:
         avail_kb = 0
         for line in open("/proc/meminfo"):
             if line.startswith("MemAvailable"):
                 avail_kb = int(line.split()[1])
-        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
         host_gib = min(len(my_models) * model_bytes / 2**30 * 1.02 + 1, avail_kb / 2**20 * 0.7 / max(local_world, 1))
-    max_conc = 32 if graph_man else (1 << 20)  # configs[1]: "HBM cache holds 32 models"
     cfg = {"modelProvider.type": "synthetic", "modelProvider.synthetic.dims": dims,
            "modelProvider.synthetic.count": wl["n_models"], "modelProvider.synthetic.namePrefix": "m",
-           "modelProvider.synthetic.threads": max(1, min(32, effective_cpus() // max(int(os.environ.get("LOCAL_WORLD_SIZE", world)), 1))),
+           "modelProvider.synthetic.threads": max(1, min(32, effective_cpus() // max(local_world, 1))),
            "gpu.devices": [local], "gpu.arenaBytes": arena, "gpu.maxBatch": 64, "gpu.maxRequestRows": 4096,
-           "gpu.stagingSlots": 4, "modelCache.size": int(host_gib * 2**30), "serving.maxConcurrentModels": max_conc,
-           # routing is done above with the library's ring + picker over the GLOBAL member list; this rank's
-           # server only ever sees the requests it owns, so its own ring has a single member
-           "proxy.replicasPerModel": 1, "gpu.members": [wl["members"][rank]], "gpu.localMembers": [wl["members"][rank]],
+           "gpu.stagingSlots": 4, "modelCache.size": int(host_gib * 2**30), "serving.maxConcurrentModels": 1 << 20,
+           # routing is done above with the library's ring + picker over the GLOBAL member list (identical on every rank);
+           # requests are handed to the cache tier of the chosen member (tfsc_predict_member / tfsc_predict_device)
+           "proxy.replicasPerModel": wl["replicas"], "gpu.members": wl["members"], "gpu.localMembers": [wl["members"][rank]],
            "proxy.seed": 1, "proxy.replicaPick": "first"}
-    if graph_man:
-        cfg.update({"modelProvider.synthetic.template": "manifest", "modelProvider.synthetic.manifest": graph_man,
-                    "gpu.arenaBytes": min(arena, 16 << 30), "gpu.maxBatch": 16, "gpu.maxRequestRows": 256})
+    win_slot = 128 << 10
+    if world > 1:
+        sock_dir = os.environ.get("TFSC_SOCK_DIR", f"/tmp/tfsc_fwd_{os.environ.get('MASTER_PORT', '0')}")
+        os.makedirs(sock_dir, exist_ok=True)
+        # window: [x rows | y rows] of one tick's forwarded requests in the value region; slots of 128 KB for the e2e region
+        n_slots = max(512, (2 * args.tick * max(inb, outb) + win_slot - 1) // win_slot + 8)
+        cfg.update({"cluster.rank": rank, "cluster.endpoints": [os.path.join(sock_dir, f"r{r}.sock") for r in range(world)],
+                    "cluster.slotBytes": win_slot, "cluster.windowSlots": int(n_slots), "proxy.grpcTimeout": 60.0})
     srv = t.Server(cfg)
 
     # page every model this rank owns into HBM once (cold loads are not part of the steady-state metric;
@@ -353,6 +441,8 @@ def run_b200(args):
     max_rows = args.tick * 4
     x_dev = torch.randn(max_rows, in_dim, device="cuda", dtype=torch.float32)
     y_dev = torch.empty(max_rows, out_dim, device="cuda", dtype=torch.float32)
+    xb_dev = torch.empty(max_rows, in_dim, device="cuda", dtype=torch.float32)    # gathered batches (groups with forwarded rows)
+    yb_dev = torch.empty(max_rows, out_dim, device="cuda", dtype=torch.float32)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():
@@ -361,24 +451,65 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # forward windows: mine holds the rows that ENTER here for other owners; the peers' windows are mapped (CUDA IPC)
+    pwin = {}
+    if world > 1:
+        _r, my_win, my_win_bytes, _slot = srv.fwd_window()
+        y_base = (my_win_bytes // 2) & ~255                     # value region layout: x rows from 0, y rows from y_base
+        assert args.tick * inb <= y_base and args.tick * outb <= my_win_bytes - y_base
+        _lib.check(_lib.lib.tfsc_device_memcpy(my_win, x_dev.data_ptr(), min(args.tick * inb, x_dev.numel() * 4)))
+        barrier()
+        for p in range(world):
+            if p != rank:
+                pwin[p] = srv.fwd_peer_window(p)[0]
+        barrier()
+
     # the request trace of every value-region step is grouped before the clock starts: the timed loop is route ->
-    # ensure-resident -> predict launches only, not numpy bookkeeping of the synthetic trace
-    pre_groups = {s: step_groups(wl, rank, s, tick_global) for s in range(W + K)}
+    # ensure-resident -> gather -> predict launches -> scatter only, not numpy bookkeeping of the synthetic trace
+    SegArr = _lib.TfscCopySeg
+    plans = {}
+    for s in range(W + K):
+        groups = step_plan(wl, rank, s, tick_global)
+        launches, gsegs, ssegs = [], [], []
+        loff = boff = 0
+        fwd_rows = 0
+        for m, n_local, fl in groups:
+            n = n_local + len(fl)
+            if not fl:
+                launches.append((f"m{m}".encode(), n, x_dev.data_ptr() + loff * inb, y_dev.data_ptr() + loff * outb))
+                loff += n
+                continue
+            # a group with forwarded rows is assembled in one batch buffer (as the batcher does): local rows + peer rows
+            xb, yb = xb_dev.data_ptr() + boff * inb, yb_dev.data_ptr() + boff * outb
+            if n_local:
+                gsegs.append((x_dev.data_ptr() + loff * inb, xb, n_local * inb))
+                ssegs.append((yb, y_dev.data_ptr() + loff * outb, n_local * outb))
+                loff += n_local
+            for j, (p, k) in enumerate(fl):
+                gsegs.append((pwin[p] + k * inb, xb + (n_local + j) * inb, inb))                      # NVLink read
+                ssegs.append((yb + (n_local + j) * outb, pwin[p] + y_base + k * outb, outb))          # NVLink write
+            launches.append((f"m{m}".encode(), n, xb, yb))
+            boff += n
+            fwd_rows += len(fl)
+        ga = (SegArr * len(gsegs))(*[SegArr(a, b, c) for a, b, c in gsegs]) if gsegs else None
+        sa = (SegArr * len(ssegs))(*[SegArr(a, b, c) for a, b, c in ssegs]) if ssegs else None
+        plans[s] = dict(groups=[(m, nl + len(fl)) for m, nl, fl in groups], launches=launches, gather=ga, n_g=len(gsegs),
+                        scatter=sa, n_s=len(ssegs), fwd_rows=fwd_rows)
+    lib = _lib.lib
+    h = srv._h
 
     def device_step(step):
-        mine, groups = pre_groups[step] if step in pre_groups else step_groups(wl, rank, step, tick_global)
-        if graph_man:
-            # cache under pressure: one fetchModel per REQUEST in arrival order, so the LRU sees real recency
-            # (hit / reload accounting as in cachemanager.go:91-152); page-ins run on the copy stream
-            for m in mine.tolist():
-                srv.ensure_async(0, f"m{m}", 1)
-        off = 0
-        for m, rows in groups:
-            if not graph_man:
-                srv.ensure_async(0, f"m{m}", 1)  # route -> ensure-resident (all hits once the shard is resident)
-            srv.predict_device(0, f"m{m}", 1, x_dev.data_ptr() + off * in_dim * 4, rows, y_dev.data_ptr() + off * out_dim * 4, sptr)
-            off += rows
-        return groups
+        p = plans[step]
+        if p["n_g"]:
+            _lib.check(lib.tfsc_k_copy_segments(p["gather"], p["n_g"], sptr))
+        for name, rows, xp, yp in p["launches"]:
+            lib.tfsc_model_ensure_async(h, 0, name, 1)      # route -> ensure-resident (all hits once the shard is resident)
+            rc = lib.tfsc_predict_device(h, 0, name, 1, xp, rows, yp, sptr)
+            if rc < 0:
+                _lib.check(rc, "predict_device")
+        if p["n_s"]:
+            _lib.check(lib.tfsc_k_copy_segments(p["scatter"], p["n_s"], sptr))
+        return p
 
     # ---- value: inputs resident in HBM ----------------------------------------------------------
     for s in range(W):
@@ -398,23 +529,21 @@ def run_b200(args):
     nvml = NvmlSampler(local, period_s=0.1)   # every rank watches its own GPU
     if "nvml" in args.samplers:
         nvml.start()
-    launches0 = _lib.lib.tfsc_kernel_launches()
+    launches0 = lib.tfsc_kernel_launches()
     st0 = srv.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    alg_bytes, n_req, n_dense = 0, 0, 0
+    alg_bytes, n_req, n_dense, fwd_rows_value = 0, 0, 0, 0
     t_host0 = time.perf_counter()
     t_wall0 = time.time()
     for s in range(W, W + K):
-        groups = device_step(s)
-        if graph_man:
-            b, l = 0, 76 * len(groups)
-        else:
-            b, l = algorithmic_bytes(groups, dims)
+        p = device_step(s)
+        b, l = algorithmic_bytes(p["groups"], dims)
         alg_bytes += b
         n_dense += l
-        n_req += sum(r for _m, r in groups)
+        n_req += sum(r for _m, r in p["groups"])
+        fwd_rows_value += p["fwd_rows"]
     ev1.record(stream)
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     barrier()
@@ -422,44 +551,52 @@ def run_b200(args):
     nvml.mark(t_wall0, time.time())
     elapsed_ms = ev0.elapsed_time(ev1)
     my_elapsed_ms, my_req = elapsed_ms, n_req
-    launches = _lib.lib.tfsc_kernel_launches() - launches0
+    launches = lib.tfsc_kernel_launches() - launches0
     st1 = srv.stats()
 
-    # ---- e2e: host buffers through tfsc_predict (C ABI), closed-loop clients ----------------------
+    # ---- e2e: host buffers through the C ABI, closed-loop clients ----------------------------------------------
     lg = C.CDLL(os.path.join(ROOT, "tools", "libtfsc_loadgen.so"))
     lg.tfsc_loadgen_run.restype = C.c_int64
     names = b"".join(f"m{j}".encode().ljust(16, b"\0") for j in range(wl["n_models"]))
     n_inputs = 256
     inputs_h = torch.randn(n_inputs, in_dim).pin_memory()
     outputs_h = torch.empty(args.clients, out_dim).pin_memory()
-    predict_ptr = C.cast(_lib.lib.tfsc_predict, C.c_void_p)
+    predict_ptr = C.cast(lib.tfsc_predict, C.c_void_p)
+    member_ptr = C.cast(lib.tfsc_predict_member, C.c_void_p)
 
-    def e2e_run(step_lo, step_hi, want_lat, clients=None, limit=None):
+    def e2e_requests(step_lo, step_hi, trace=None):
+        """requests that ENTER at this rank in the step range: (model ids, member = owner rank chosen by the front tier)"""
+        lo, hi = step_lo * tick_global, step_hi * tick_global
+        sel = wl["ingress"][lo:hi] == rank
+        tr = (trace if trace is not None else wl["trace"])[lo:hi][sel]
+        return tr.astype(np.int32), wl["dest"][lo:hi][sel].astype(np.int32)
+
+    def e2e_run(req, mem, want_lat, clients=None):
         clients = clients or args.clients
-        req = np.concatenate([step_groups(wl, rank, s, tick_global)[0] for s in range(step_lo, step_hi)]).astype(np.int32)
-        if limit:
-            req = req[:limit]
-        lat = np.zeros(len(req), np.float32)
+        req, mem = np.ascontiguousarray(req), np.ascontiguousarray(mem)
+        lat = np.zeros(max(1, len(req)), np.float32)
         el = C.c_double()
-        failed = lg.tfsc_loadgen_run(predict_ptr, C.c_void_p(srv._h), names, 16, b"1", req.ctypes.data_as(C.c_void_p),
+        failed = lg.tfsc_loadgen_run(predict_ptr, C.c_void_p(h), names, 16, b"1", req.ctypes.data_as(C.c_void_p),
                                      C.c_int64(len(req)), C.c_void_p(inputs_h.data_ptr()), C.c_int64(n_inputs), in_dim,
                                      C.c_void_p(outputs_h.data_ptr()), out_dim, clients,
-                                     lat.ctypes.data_as(C.c_void_p) if want_lat else None, C.byref(el))
-        return len(req), failed, el.value, lat
+                                     lat.ctypes.data_as(C.c_void_p) if want_lat else None, C.byref(el),
+                                     member_ptr, mem.ctypes.data_as(C.c_void_p))
+        return len(req), failed, el.value, lat[:len(req)]
 
     e0 = W + K
     if not args.skip_e2e:
-        e2e_run(e0, e0 + W, False)
+        e2e_run(*e2e_requests(e0, e0 + W), False)
     barrier()
     ste0 = srv.stats()
     if args.skip_e2e:
         n_e2e, failed, el_s, lat = 0, 0, 1.0, np.zeros(1, np.float32)
     else:
         t_e0 = time.time()
-        n_e2e, failed, el_s, lat = e2e_run(e0 + W, e0 + W + e2e_steps, True)
+        n_e2e, failed, el_s, lat = e2e_run(*e2e_requests(e0 + W, e0 + W + e2e_steps), True)
         sampler.mark(t_e0, time.time())
         nvml.mark(t_e0, time.time())
     torch.cuda.synchronize()
+    barrier()
     ste1 = srv.stats()
     clocks = sampler.stop()
     my_nvml = nvml.stop()
@@ -468,36 +605,93 @@ def run_b200(args):
         clocks["source"] = "nvml"
     if my_nvml:
         clocks["nvml"] = my_nvml
-    # light-load latency probe (north_star: cache-hit p50 < 5 ms): same trace, few closed-loop clients
-    light = None
-    if args.light_clients > 0 and not args.skip_e2e:
-        n_l, f_l, el_l, lat_l = e2e_run(e0 + W, e0 + W + e2e_steps, True, clients=args.light_clients, limit=args.light_clients * 64)
-        light = {"clients_per_gpu": args.light_clients, "requests": int(n_l), "qps_rank0": round(n_l / el_l, 1),
-                 "p50_ms": round(float(np.percentile(lat_l, 50)) / 1e3, 3), "p99_ms": round(float(np.percentile(lat_l, 99)) / 1e3, 3)}
+
+    def allsum(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        tt = torch.tensor(vals, device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        return [float(v) for v in tt]
+
+    def allmax(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        tt = torch.tensor(vals, device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return [float(v) for v in tt]
+
+    # ---- latency-bounded throughput: closed-loop client sweep (north_star: cache-hit p50 < 5 ms) -----------------
+    sweep, light = [], None
+    if not args.skip_e2e and not args.no_extras:
+        req_all, mem_all = e2e_requests(e0 + W, e0 + W + e2e_steps)
+        for c in (args.light_clients, 64, 128, 256, 512):
+            if c <= 0 or c > args.clients:
+                continue
+            n_l = min(len(req_all), c * 40)
+            barrier()
+            _n, f_l, el_l, lat_l = e2e_run(req_all[:n_l], mem_all[:n_l], True, clients=c)
+            qps_all, = allsum([n_l / el_l])
+            p50_w, p99_w = allmax([float(np.percentile(lat_l, 50)) / 1e3, float(np.percentile(lat_l, 99)) / 1e3])
+            sweep.append({"clients_per_gpu": c, "qps": round(qps_all, 1), "p50_ms": round(p50_w, 3), "p99_ms": round(p99_w, 3),
+                          "failed": int(f_l)})
+        if sweep:
+            light = dict(sweep[0])
+    ok = [p for p in sweep if p["p50_ms"] < 5.0]
+    qps_at_p50_5ms = max(ok, key=lambda p: p["qps"]) if ok else None
+
+    # ---- cache under pressure: resident cap below the working set, uniform storm (configs[4]) ---------------------
+    pressure = None
+    if not args.skip_e2e and not args.no_extras and len(my_models) > args.pressure_resident:
+        from tools.traces import uniform_trace
+        barrier()
+        srv.set_max_resident(0, args.pressure_resident)
+        n_p = 3 * tick_global
+        utrace = np.asarray(my_models, np.int64)[uniform_trace(len(my_models), n_p, seed=7 + rank)]   # this rank's own models
+        sp0 = srv.stats()
+        tp0 = time.time()
+        _n, f_p, el_p, lat_p = e2e_run(utrace.astype(np.int32), np.full(n_p, rank, np.int32), True, clients=min(args.clients, 256))
+        sp1 = srv.stats()
+        srv.set_max_resident(0, 1 << 20)
+        tot = max(1, sp1["cache_total"] - sp0["cache_total"])
+        h2d = sp1["h2d_weight_bytes"] - sp0["h2d_weight_bytes"]
+        qps_p, h2d_all = allsum([n_p / el_p, h2d / el_p / 1e9])
+        p50_p, p99_p = allmax([float(np.percentile(lat_p, 50)) / 1e3, float(np.percentile(lat_p, 99)) / 1e3])
+        pressure = {"trace": f"uniform over this rank's {len(my_models)} models, 256 clients per GPU", "resident_cap": args.pressure_resident,
+                    "ideal_hit_pct": round(100.0 * args.pressure_resident / len(my_models), 1), "requests_per_gpu": int(n_p),
+                    "qps": round(qps_p, 1), "hit_pct_rank0": round(100.0 * (sp1["cache_hits_total"] - sp0["cache_hits_total"]) / tot, 2),
+                    "reloads_rank0": int(tot - (sp1["cache_hits_total"] - sp0["cache_hits_total"]) - (sp1["cache_misses_total"] - sp0["cache_misses_total"])),
+                    "evictions_hbm_rank0": int(sp1["evictions_hbm"] - sp0["evictions_hbm"]),
+                    "h2d_weight_GBps_all_gpus": round(h2d_all, 2), "h2d_weight_GBps_per_gpu": round(h2d_all / world, 2),
+                    "pcie_roofline_GBps_per_gpu": 55.0, "load_stall_p50_ms": round(p50_p, 3), "load_stall_p99_ms": round(p99_p, 3),
+                    "failed": int(f_p), "seconds": round(time.time() - tp0, 2)}
+        # bring the shard back for anything that follows
+        for m in my_models:
+            srv.ensure_async(0, f"m{m}", 1)
+        srv.sync(0)
+
     per_rank = None
+    fwd_out = ste1["fwd_out_requests"] - ste0["fwd_out_requests"]
+    fwd_bytes = (ste1["fwd_peer_bytes_read"] - ste0["fwd_peer_bytes_read"]) + (ste1["fwd_peer_bytes_written"] - ste0["fwd_peer_bytes_written"])
     if world > 1:
         nv = my_nvml or {}
         rmask = sum(b for b, n in NvmlSampler.REASONS.items() if n in nv.get("reasons", []))
         diag = torch.tensor([my_elapsed_ms, host_enqueue_ms, my_req, n_dense, nv.get("sm_mhz", -1), nv.get("sm_min_mhz", -1),
-                             nv.get("power_w", -1), rmask], device="cuda", dtype=torch.float64)
+                             nv.get("power_w", -1), rmask, n_e2e, el_s], device="cuda", dtype=torch.float64)
         allr = [torch.zeros_like(diag) for _ in range(world)]
         dist.all_gather(allr, diag)
         per_rank = [{"device_ms": round(float(v[0]), 2), "host_enqueue_ms": round(float(v[1]), 2), "requests": int(v[2]),
-                     "launches": int(v[3]), "sm_mhz": float(v[4]), "sm_min_mhz": float(v[5]), "power_w": float(v[6]),
-                     "reasons": sorted(n for b, n in NvmlSampler.REASONS.items() if int(v[7]) & b)} for v in allr]
-        tt = torch.tensor([elapsed_ms, el_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed_ms, el_s = float(tt[0]), float(tt[1])
-        cc = torch.tensor([n_req, n_e2e, launches, alg_bytes, failed, n_dense], device="cuda", dtype=torch.float64)
-        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
-        n_req_all, n_e2e_all, launches_all, failed_all = int(cc[0]), int(cc[1]), int(cc[2]), int(cc[4])
-        alg_bytes, n_dense = float(cc[3]) / world, int(cc[5])  # per-GPU average bytes over the max-over-ranks time
-    else:
-        n_req_all, n_e2e_all, launches_all, failed_all = n_req, n_e2e, launches, failed
+                     "launches": int(v[3]), "us_per_launch": round(float(v[0]) * 1e3 / max(1.0, float(v[3])), 2),
+                     "sm_mhz": float(v[4]), "sm_min_mhz": float(v[5]), "power_w": float(v[6]),
+                     "reasons": sorted(n for b, n in NvmlSampler.REASONS.items() if int(v[7]) & b),
+                     "e2e_requests": int(v[8]), "e2e_s": round(float(v[9]), 3)} for v in allr]
+    elapsed_ms, el_s = allmax([elapsed_ms, el_s])
+    n_req_all, n_e2e_all, launches_all, alg_sum, failed_all, n_dense, fwd_rows_all, fwd_out_all, fwd_bytes_all = allsum(
+        [n_req, n_e2e, launches, alg_bytes, failed, n_dense, fwd_rows_value, fwd_out, fwd_bytes])
+    alg_bytes = alg_sum / world   # per-GPU average bytes over the max-over-ranks time
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    peaks = _peaks()
+    if "hbm_gbs" in peaks:
+        peak, peak_src = peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
     achieved = alg_bytes / (elapsed_ms * 1e-3) / 1e9  # this rank's dense launches are the whole timed region
@@ -507,24 +701,26 @@ def run_b200(args):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
 
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not graph_man:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference(args.cpu_sample, dims, warm=4)
 
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extras and not args.skip_e2e:
+        srv.close()
+        srv = None
+        extra = {}
+        for kind in ("resnet50", "bert_base"):
+            try:
+                extra[kind] = graph_model_speed(kind)
+            except Exception as ex:  # an extra line must never cost the headline
+                extra[kind] = {"error": repr(ex)[:200]}
+
     roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-            "traffic": traffic, "kernel": "dense_stream_kernel<R> (<=8 rows) + dense_tc_kernel<RP> (9..64 rows, tcgen05 3xTF32): fused xW+b+ReLU, split-K",
-            "peak_source": peak_src, "launches_timed": n_dense, "avg_launch_us": round(elapsed_ms * 1e3 * world / max(1, n_dense), 2),
-            "note": "per-GPU average algorithmic bytes / max-over-ranks device time"}
-    workload = (f"BASELINE configs[2] per-GPU shard: {args.models_per_gpu} per-tenant 3-layer MLP "
-                f"({'x'.join(map(str, dims))} fp32, {model_bytes} B) per GPU, Zipf alpha=1.0, ring replicas={wl['replicas']} "
-                f"(replica pick: {wl['pick_policy']}); at 8 GPUs = configs[2] (1000 models)")
-    if graph_man:
-        tf_peak = json.load(open(peaks_path)).get("bf16_tflops_sustained", 1405.4) if os.path.exists(peaks_path) else 1400.0
-        tfl = 8.2e9 * n_req_all / world / (elapsed_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": round(tfl, 2), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(tfl / tf_peak, 5), "traffic": None,
-                "kernel": "gemm_tc_kernel (im2col + tcgen05 3xTF32 GEMM; CUDA-core gemm_f32_kernel for M < 64 / N % 32 != 0 layers)",
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)", "note": "8.2 GFLOP per 224x224 image"}
-        workload = (f"BASELINE configs[1]: {args.models_per_gpu} ResNet-50 (v1.5, 25.5 M params, {model_bytes} B) per GPU, Zipf alpha=1.0, "
-                    f"HBM cache holds {max_conc} models (serving.maxConcurrentModels), host tier holds all, 1 image per request")
+            "traffic": traffic,
+            "kernel": "dense_cluster_kernel<R> (<=8 rows, 2-CTA clusters, TMA ring, DSMEM K-fold, PDL) + dense_tc_kernel<RP> (9..64 rows, tcgen05 3xTF32, PDL): fused xW+b+ReLU",
+            "peak_source": peak_src, "launches_timed": int(n_dense), "avg_launch_us": round(elapsed_ms * 1e3 * world / max(1, n_dense), 2),
+            "note": "per-GPU average algorithmic bytes / max-over-ranks device time; gather / scatter launches of forwarded rows are inside the timed region"}
+    workload = workload_string(args.models_per_gpu, dims, wl["replicas"], wl["pick_policy"])
     if rank == 0:
         value = n_req_all / (elapsed_ms * 1e-3)
         e2e_val = n_e2e_all / el_s
@@ -534,27 +730,43 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload,
                        "models_total": wl["n_models"], "tick_requests_per_gpu": args.tick, "max_rows_per_pass": "8 (SIMT) / 64 (tcgen05 3xTF32)",
-                       "l2": ("L2 flushed before timing; 100 models x 102 MB of weights cycle through per GPU (> L2)" if graph_man else
-                              "inputs larger than L2 (>=1 GB of weights streamed per model pass); L2 flushed before timing"),
-                       "arena_gib": round(arena / 2**30, 1), "host_tier_gib": round(host_gib, 1), "cold_load_s": round(load_s, 1)},
+                       "l2": "inputs larger than L2 (>=1 GB of weights streamed per model pass); L2 flushed before timing",
+                       "arena_gib": round(arena / 2**30, 1), "host_tier_gib": round(host_gib, 1), "cold_load_s": round(load_s, 1),
+                       "preheat_s": args.preheat_s, "samplers": args.samplers},
             "e2e": {"value": round(e2e_val, 1), "unit": "req/s",
                     "h2d_bytes_per_step": int((ste1["h2d_input_bytes"] - ste0["h2d_input_bytes"] + ste1["h2d_weight_bytes"] - ste0["h2d_weight_bytes"]) / e2e_steps),
                     "d2h_bytes_per_step": int((ste1["d2h_output_bytes"] - ste0["d2h_output_bytes"]) / e2e_steps),
-                    "clients_per_gpu": args.clients, "steps": e2e_steps, "failed": failed_all,
+                    "transfer": "inputs: client memcpy into pinned staging, gather kernel reads it over PCIe; results: scatter kernel writes pinned staging (bytes counted per request row, rank 0)",
+                    "clients_per_gpu": args.clients, "steps": e2e_steps, "failed": int(failed_all),
                     "p50_ms": round(float(np.percentile(lat, 50)) / 1e3, 3), "p99_ms": round(float(np.percentile(lat, 99)) / 1e3, 3),
                     "mean_batch_rows": round((ste1["batched_rows"] - ste0["batched_rows"]) / max(1, ste1["batches"] - ste0["batches"]), 2),
-                    "light_load": light},
+                    "light_load": light, "sweep": sweep,
+                    "qps_at_p50_5ms": qps_at_p50_5ms},
             "hbm_cache_hit_pct": round(100.0 * (st1["cache_hits_total"] - st0["cache_hits_total"]) / max(1, st1["cache_total"] - st0["cache_total"]), 2),
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": roof,
         }
+        if world > 1:
+            line["forward"] = {"fraction": fwd_frac,
+                               "value_region": {"forwarded_requests_per_step": round(fwd_rows_all / K, 1),
+                                                "nvlink_bytes_per_step": int(fwd_rows_all * (inb + outb) / K)},
+                               "e2e_region": {"forwarded_requests": int(fwd_out_all), "nvlink_bytes_per_step": int(fwd_bytes_all / e2e_steps),
+                                              "mean_rtt_ms_rank0": round(1e3 * (ste1["fwd_rtt_seconds_sum"] - ste0["fwd_rtt_seconds_sum"]) / max(1, fwd_out), 3)},
+                               "path": "ingress window (HBM, CUDA IPC) -> owner gather kernel over NVLink -> kernels -> scatter kernel over NVLink; control: unix socket"}
+        if pressure:
+            line["cache_pressure"] = pressure
+        if extra:
+            line["extra"] = extra
         if per_rank:
             line["per_rank"] = per_rank
         if cpu_base:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
-    srv.close()
+    if world > 1:
+        dist.barrier()    # nobody closes its window while a peer may still use it
+    if srv is not None:
+        srv.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -654,13 +866,12 @@ def run_reference(args):
     # each "step" is a bounded sample of the workload; K steps + W warm-up end within minutes
     per_step = max(4, args.cpu_sample // 4)
     base = cpu_reference(per_step * args.steps, dims, warm=max(1, per_step * args.warmup // 4))
-    model_bytes = sum(dims[i] * dims[i + 1] * 4 + dims[i + 1] * 4 for i in range(len(dims) - 1))
     line = {"impl": "reference", "metric": "predict_qps", "value": base["value"], "unit": "req/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * base["seconds"] / args.steps, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2] per-GPU shard: {MODELS_PER_GPU} per-tenant 3-layer MLP "
-                                   f"({'x'.join(map(str, dims))} fp32, {model_bytes} B) per GPU, Zipf alpha=1.0; CPU reference path, "
-                                   f"bounded sample of {per_step} requests per step"},
+            "config": {"workload": workload_string(args.models_per_gpu, dims, min(2, world), args.replica_pick),
+                       "reference_sample": f"CPU reference path, bounded sample of {per_step} requests per step; at N > 1 still ONE CPU "
+                                           f"process on rank 0 (the reference's CPU path does not use the GPUs), ms_per_step = sample time / steps"},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "req/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

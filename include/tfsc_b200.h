@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TFSC_ABI_VERSION 1
+#define TFSC_ABI_VERSION 2
 
 /* error codes; the gRPC status each one maps to is given in parentheses */
 #define TFSC_OK 0
@@ -78,7 +78,8 @@ int tfsc_ring_points(const tfsc_ring* r);               /* ring points (<= 20 * 
 int tfsc_ring_getn(const tfsc_ring* r, const char* key, int n, char* buf, size_t cap);
 /* Replica choice among the GetN candidates: "random" = the reference (taskhandler.go:91), "first" = primary,
  * "hot-spread" = primary unless the key's recent request share exceeds hot_fraction / members (then random),
- * "balanced" = hot-spread + least-loaded-replica binding (tfsc_picker_pick_ids).
+ * "balanced" = hot-spread + least-loaded-replica binding (tfsc_picker_pick_ids), "hash" = crc32(key) mod replicas
+ * (stateless: independent processes agree on the replica of a key).
  * Deterministic for a given seed and call sequence. tfsc_picker_pick returns an index in [0, n_replicas). */
 typedef struct tfsc_picker tfsc_picker;
 tfsc_picker* tfsc_picker_new(const char* policy, uint64_t seed, double hot_fraction);
@@ -163,6 +164,9 @@ typedef struct tfsc_stats {
   int64_t kernel_launches, batches, batched_rows;
   int64_t arena_bytes_used, arena_bytes_capacity, resident_models, host_models;
   double cache_duration_seconds_sum, cache_fetch_duration_seconds_sum;
+  /* forward hop (a6): requests sent to / received from other ranks, bytes the owner moved over NVLink */
+  int64_t fwd_out_requests, fwd_in_requests, fwd_out_failures, fwd_peer_bytes_read, fwd_peer_bytes_written;
+  double fwd_rtt_seconds_sum;
 } tfsc_stats;
 
 tfsc_server* tfsc_server_create(const char* config_json); /* main.go:45-113 */
@@ -193,6 +197,28 @@ int tfsc_host_list(tfsc_server* s, int node, char* buf, size_t cap);
  * `version` is the verbatim string ("00000123" routes differently from "123": reference quirk). */
 int tfsc_predict(tfsc_server* s, const char* model_name, const char* version,
                  const tfsc_tensor* in, int n_in, tfsc_tensor* out, int n_out);
+/* tfsc_predict with a deadline (absolute, on the clock of tfsc_now_ns() = CLOCK_MONOTONIC; 0 = none): a request still
+ * queued when its deadline passes is answered TFSC_E_TIMEOUT without being launched (grpc deadline / proxy.grpcTimeout). */
+int tfsc_predict_deadline(tfsc_server* s, const char* model_name, const char* version,
+                          const tfsc_tensor* in, int n_in, tfsc_tensor* out, int n_out, int64_t deadline_ns);
+int64_t tfsc_now_ns(void);
+/* The cache tier of one member, without the ring lookup (the reference's second tier: cachemanager.ServeRest / ServeGrpc on
+ * cacheRestPort / cacheGrpcPort, cmd/taskhandler/main.go:60-84 -- a request that reaches a cache node is served there):
+ * `member` indexes the current member list ("gpu.members" / tfsc_server_set_members order). A local member runs on its node;
+ * a member of another rank takes the forward hop. For callers that route themselves (tfsc_route, or a front load balancer). */
+int tfsc_predict_member(tfsc_server* s, int member, const char* model_name, const char* version,
+                        const tfsc_tensor* in, int n_in, tfsc_tensor* out, int n_out, int64_t deadline_ns);
+/* Asynchronous Predict: no OS thread is parked per in-flight request (a Go handler keeps a goroutine, not an M).
+ *   submit: route -> ensure-resident (may block on a cold load of THIS model only) -> signature checks -> the input rows are
+ *           copied to pinned staging, so `in` may be reused at once. out[0].data / nbytes is the caller's result buffer.
+ *   wait  : timeout_ns < 0 blocks; >= 0 waits at most that long and answers TFSC_E_TIMEOUT while the request is still in
+ *           flight (the ticket stays valid). On success out[0] holds dtype / shape / nbytes and the data.
+ *   release: frees the ticket (waits for the request to retire first if it is still in flight). */
+typedef struct tfsc_ticket tfsc_ticket;
+int tfsc_predict_submit(tfsc_server* s, const char* model_name, const char* version, const tfsc_tensor* in, int n_in,
+                        tfsc_tensor* out, int n_out, int64_t deadline_ns, tfsc_ticket** ticket);
+int tfsc_predict_wait(tfsc_ticket* ticket, int64_t timeout_ns);
+void tfsc_predict_release(tfsc_ticket* ticket);
 /* Same, wire level: serialized tensorflow.serving.PredictRequest in, PredictResponse out
  * (library-owned; tfsc_free). This is what a cgo Predict handler calls. */
 int tfsc_grpc_predict(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len);
@@ -208,6 +234,22 @@ int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const 
 int tfsc_predict_device(tfsc_server* s, int node, const char* model_name, int64_t version,
                         const void* x, int64_t rows, void* y, void* stream);
 int tfsc_node_sync(tfsc_server* s, int node);
+/* serving.maxConcurrentModels of one node at run time (takes effect at the next reload: cachemanager.go:167-170) */
+int tfsc_node_set_max_resident(tfsc_server* s, int node, int max_concurrent_models);
+
+/* ---------------------------------------------------------------- a6 / X7: forward hop between processes ------
+ * One process per GPU (torchrun): config keys "cluster.rank", "cluster.endpoints" (one unix-socket path per entry of
+ * "gpu.members", same order), "cluster.slotBytes", "cluster.windowSlots". A Predict whose ring owner is another rank is
+ * forwarded there like restDirector / grpcDirector do (taskhandler.go:95-147), except that only a ~100-byte control message
+ * crosses the socket: the request rows sit in this rank's FORWARD WINDOW (HBM exported with CUDA IPC), the owner's gather /
+ * scatter kernels (or its first / last layer, with tfsc_predict_device) read x and write y there over NVLink.
+ * tfsc_fwd_window: this rank's window (device pointer, bytes, slot size); returns the rank.
+ * tfsc_fwd_peer_window: rank `peer_rank`'s window mapped into this process (dials the peer on first use). */
+int tfsc_fwd_window(tfsc_server* s, void** dev_ptr, size_t* bytes, size_t* slot_bytes);
+int tfsc_fwd_peer_window(tfsc_server* s, int peer_rank, void** dev_ptr, size_t* bytes);
+/* synchronous copy between any two addresses of the unified address space (host, this GPU, a mapped peer window): how a
+ * host program without its own CUDA binding fills / reads window slots for tfsc_predict_device */
+int tfsc_device_memcpy(void* dst, const void* src, size_t nbytes);
 int tfsc_get_stats(tfsc_server* s, int node, tfsc_stats* out); /* node = -1: sum over nodes */
 /* number of kernels launched by this library since load (bench gpu_launches) */
 int64_t tfsc_kernel_launches(void);
@@ -231,6 +273,16 @@ int tfsc_k_dense_variant(int variant, const float* x, const float* w, const floa
  * automatically for more than 8 rows; this entry exists for parity tests and roofline timing. */
 int tfsc_k_dense_tc(const float* x, const float* w, const float* b, float* y, int rows, int k, int n, int relu,
                     float* workspace, size_t workspace_bytes, void* stream);
+
+/* X6 (+ X7): batch gather / scatter as one kernel over a table of segments. src / dst may be pinned host memory, local HBM or
+ * a peer's forward window (NVLink): this is the kernel the batcher uses to assemble a batch from its requests' rows and to
+ * hand the result rows back (csrc/nn_kernels.cu copy_segments_kernel). */
+typedef struct tfsc_copy_seg {
+  const void* src;
+  void* dst;
+  uint64_t bytes;
+} tfsc_copy_seg;
+int tfsc_k_copy_segments(const tfsc_copy_seg* segs, int n, void* stream);
 
 /* X4/X5 building blocks of the graph executor (conv nets), fp32, row-major / NHWC. act: 0 none, 1 relu, 2 gelu.
  * C[M,N] = act(A[M,K] (row stride lda) * B[K,N] + bias[N] (+ R[M,N])); bias / R may be NULL. */

@@ -28,7 +28,7 @@ def test_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(t._lib.LIB_PATH)
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.tfsc_abi_version() == 1
+    assert lib.tfsc_abi_version() == int(re.search(r"#define TFSC_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "tfsc_b200.h")).read()).group(1)) == 2
 
 
 def test_no_device_fails_loudly():

@@ -36,7 +36,9 @@ class TfscStats(C.Structure):
         "evictions_host", "evictions_hbm", "h2d_weight_bytes", "h2d_input_bytes", "d2h_output_bytes",
         "kernel_launches", "batches", "batched_rows",
         "arena_bytes_used", "arena_bytes_capacity", "resident_models", "host_models")] + [
-        ("cache_duration_seconds_sum", C.c_double), ("cache_fetch_duration_seconds_sum", C.c_double)]
+        ("cache_duration_seconds_sum", C.c_double), ("cache_fetch_duration_seconds_sum", C.c_double)] + [
+        (n, C.c_int64) for n in ("fwd_out_requests", "fwd_in_requests", "fwd_out_failures", "fwd_peer_bytes_read",
+                                 "fwd_peer_bytes_written")] + [("fwd_rtt_seconds_sum", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -94,10 +96,27 @@ _sig("tfsc_model_ensure_async", C.c_int, vp, C.c_int, cp, i64)
 _sig("tfsc_resident_list", C.c_int, vp, C.c_int, C.c_char_p, sz)
 _sig("tfsc_host_list", C.c_int, vp, C.c_int, C.c_char_p, sz)
 _sig("tfsc_predict", C.c_int, vp, cp, cp, C.POINTER(TfscTensor), C.c_int, C.POINTER(TfscTensor), C.c_int)
+_sig("tfsc_predict_deadline", C.c_int, vp, cp, cp, C.POINTER(TfscTensor), C.c_int, C.POINTER(TfscTensor), C.c_int, i64)
+_sig("tfsc_now_ns", i64)
+_sig("tfsc_predict_member", C.c_int, vp, C.c_int, cp, cp, C.POINTER(TfscTensor), C.c_int, C.POINTER(TfscTensor), C.c_int, i64)
+_sig("tfsc_predict_submit", C.c_int, vp, cp, cp, C.POINTER(TfscTensor), C.c_int, C.POINTER(TfscTensor), C.c_int, i64, C.POINTER(vp))
+_sig("tfsc_predict_wait", C.c_int, vp, i64)
+_sig("tfsc_predict_release", None, vp)
+_sig("tfsc_fwd_window", C.c_int, vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz))
+_sig("tfsc_fwd_peer_window", C.c_int, vp, C.c_int, C.POINTER(vp), C.POINTER(sz))
+_sig("tfsc_device_memcpy", C.c_int, vp, vp, sz)
 _sig("tfsc_grpc_predict", C.c_int, vp, vp, sz, C.POINTER(vp), C.POINTER(sz))
 _sig("tfsc_rest_handle", C.c_int, vp, cp, cp, vp, sz, C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(sz))
 _sig("tfsc_predict_device", C.c_int, vp, C.c_int, cp, i64, vp, i64, vp, vp)
 _sig("tfsc_node_sync", C.c_int, vp, C.c_int)
+_sig("tfsc_node_set_max_resident", C.c_int, vp, C.c_int, C.c_int)
+
+
+class TfscCopySeg(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes", C.c_uint64)]
+
+
+_sig("tfsc_k_copy_segments", C.c_int, C.POINTER(TfscCopySeg), C.c_int, vp)
 _sig("tfsc_get_stats", C.c_int, vp, C.c_int, C.POINTER(TfscStats))
 _sig("tfsc_kernel_launches", i64)
 _sig("tfsc_k_affine", C.c_int, vp, vp, i64, vp, vp, vp)

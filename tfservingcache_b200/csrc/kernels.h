@@ -55,6 +55,16 @@ bool gemm_tc_supported(const float* A, const float* B, const float* bias, const 
 cudaError_t launch_gemm_tc(const float* A, const float* B, const float* bias, const float* R, float* C, int M, int N, int K,
                            int lda, int act, cudaStream_t s);
 
+// X6 (+ X7): batch gather / scatter as ONE kernel over a table of (src, dst, bytes) segments. A source / destination may be
+// pinned host memory (zero-copy over PCIe: the client thread wrote it, no batcher-side memcpy, no staging copy), local HBM,
+// or another GPU's forward window mapped through CUDA IPC (the forward hop a6: NVLink loads / stores inside this kernel).
+struct CopySeg {
+  const void* src;
+  void* dst;
+  uint64_t bytes;
+};
+cudaError_t launch_copy_segments(const CopySeg* segs, int n, cudaStream_t s);
+
 int64_t kernel_launch_count();
 
 }  // namespace tfsc

@@ -389,4 +389,62 @@ cudaError_t launch_attention(const float* qkv, const int* ids, float* ctx, int B
   return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------ X6 / X7 ----
+constexpr int kCopySegMax = 64;
+struct CopySegTable {
+  const char* src[kCopySegMax];
+  char* dst[kCopySegMax];
+  unsigned long long bytes[kCopySegMax];
+};
+
+// grid = (chunks, segments). 16-byte vectors when source, destination and length allow it, 4-byte words otherwise (request
+// tensors are fp32 / int32, so lengths are multiples of 4; staging buffers and window slots are 256-byte aligned).
+__global__ void __launch_bounds__(256) copy_segments_kernel(const __grid_constant__ CopySegTable tab) {
+  const int sg = blockIdx.y;
+  const char* __restrict__ src = tab.src[sg];
+  char* __restrict__ dst = tab.dst[sg];
+  const unsigned long long bytes = tab.bytes[sg];
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long nthr = (unsigned long long)gridDim.x * blockDim.x;
+  if ((((unsigned long long)src | (unsigned long long)dst | bytes) & 15ull) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const unsigned long long n = bytes >> 4;
+    for (unsigned long long i = tid; i < n; i += nthr) d4[i] = s4[i];
+  } else if ((((unsigned long long)src | (unsigned long long)dst | bytes) & 3ull) == 0) {
+    const unsigned int* s1 = reinterpret_cast<const unsigned int*>(src);
+    unsigned int* d1 = reinterpret_cast<unsigned int*>(dst);
+    const unsigned long long n = bytes >> 2;
+    for (unsigned long long i = tid; i < n; i += nthr) d1[i] = s1[i];
+  } else {
+    for (unsigned long long i = tid; i < bytes; i += nthr) dst[i] = src[i];
+  }
+}
+
+cudaError_t launch_copy_segments(const CopySeg* segs, int n, cudaStream_t s) {
+  for (int base = 0; base < n; base += kCopySegMax) {
+    const int m = n - base < kCopySegMax ? n - base : kCopySegMax;
+    CopySegTable tab;
+    unsigned long long mx = 0;
+    for (int i = 0; i < m; ++i) {
+      tab.src[i] = static_cast<const char*>(segs[base + i].src);
+      tab.dst[i] = static_cast<char*>(segs[base + i].dst);
+      tab.bytes[i] = segs[base + i].bytes;
+      if (segs[base + i].bytes > mx) mx = segs[base + i].bytes;
+    }
+    if (mx == 0) continue;
+    // 16 KB per block keeps ~64 independent 16-byte requests per thread-block wave in flight (PCIe / NVLink latency);
+    // few blocks, no shared memory: the kernel co-resides with the weight-streaming kernels (1 CTA per SM, 544 threads)
+    unsigned long long chunks = (mx + 16383) / 16384;
+    if (chunks > 32) chunks = 32;
+    if (chunks < 1) chunks = 1;
+    copy_segments_kernel<<<dim3((unsigned)chunks, (unsigned)m), 256, 0, s>>>(tab);
+    g_launches_nn++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 }  // namespace tfsc

@@ -57,12 +57,15 @@ Node::~Node() {
   q_cv_.notify_all();
   slot_cv_.notify_all();
   if (batcher_.joinable()) batcher_.join();
+  {
+    std::lock_guard<std::mutex> lk(q_mu_);
+    batcher_done_ = true;  // only now may the completer stop: the batcher can no longer hand it a batch
+  }
+  q_cv_.notify_all();
   if (completer_.joinable()) completer_.join();
   DeviceGuard g(cfg_.device);
   cudaDeviceSynchronize();
   for (auto& s : slots_) {
-    if (s.h_in) cudaFreeHost(s.h_in);
-    if (s.h_out) cudaFreeHost(s.h_out);
     if (s.d_in) cudaFree(s.d_in);
     if (s.d_out) cudaFree(s.d_out);
     if (s.scratch) cudaFree(s.scratch);
@@ -73,6 +76,9 @@ Node::~Node() {
   }
   for (auto& kv : stream_scratch_) cudaFree(kv.second.base);
   for (auto& r : retire_) cudaEventDestroy(r.ev);
+  // every reference to a DeviceModel / HostModel must go while the pinned-block pool still exists: HostModel's release
+  // functor returns the block to pool_ (a member destroyed BEFORE retire_ / dev_ / host_ in reverse declaration order)
+  retire_.clear();
   drain_.clear();
   for (auto& kv : dev_)
     if (kv.second->ready) cudaEventDestroy(kv.second->ready);
@@ -80,6 +86,8 @@ Node::~Node() {
   host_.clear();  // returns pinned blocks to the pool
   for (auto e : event_pool_) cudaEventDestroy(e);
   for (auto& kv : pool_)
+    for (void* p : kv.second) cudaFreeHost(p);
+  for (auto& kv : stage_pool_)
     for (void* p : kv.second) cudaFreeHost(p);
   if (slab_) cudaFree(slab_);
   if (compute_) cudaStreamDestroy(compute_);
@@ -435,6 +443,22 @@ int Node::fetch(const ModelId& id, std::shared_ptr<DeviceModel>* pinned, std::st
   return outcome;
 }
 
+void Node::set_max_concurrent_models(int n) {
+  DeviceGuard g(cfg_.device);
+  std::lock_guard<std::mutex> lk(mu_);
+  cfg_.max_concurrent_models = n;
+  reap_locked();
+  // what TF-Serving does when a reload config lists fewer models: everything outside the new resident prefix unloads
+  std::set<std::pair<std::string, int64_t>> keep;
+  for (auto& m : resident_prefix_locked()) keep.insert({m.id.name, m.id.version});
+  std::vector<std::shared_ptr<DeviceModel>> drop;
+  for (auto& kv : dev_)
+    if ((kv.second->state == TFSC_STATE_AVAILABLE || kv.second->state == TFSC_STATE_LOADING) &&
+        !keep.count({kv.second->id.name, kv.second->id.version}))
+      drop.push_back(kv.second);
+  for (auto& d : drop) begin_unload_locked(d);
+}
+
 int Node::status(const ModelId& id) {
   DeviceGuard g(cfg_.device);
   std::lock_guard<std::mutex> lk(mu_);
@@ -566,8 +590,52 @@ cudaError_t Node::run_model(const DeviceModel& dm, const char* x, int64_t rows, 
   return cudaSuccess;
 }
 
-static size_t row_in_bytes(const ModelDesc& d) { return d.tmpl == Template::Affine ? 4 : (size_t)d.in_dim * 4; }
-static size_t row_out_bytes(const ModelDesc& d) { return d.tmpl == Template::Affine ? 4 : (size_t)d.out_dim * 4; }
+size_t Node::row_in_bytes(const ModelDesc& d) { return d.tmpl == Template::Affine ? 4 : (size_t)d.in_dim * 4; }
+size_t Node::row_out_bytes(const ModelDesc& d) { return d.tmpl == Template::Affine ? 4 : (size_t)d.out_dim * 4; }
+int64_t Node::now_ns() { return std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now().time_since_epoch()).count(); }
+
+// ---- pinned request staging: power-of-two size classes, reused (cudaHostAlloc costs ~100 us + a page-table walk) ----
+static size_t stage_class(size_t bytes) {
+  size_t c = 4096;
+  while (c < bytes) c <<= 1;
+  return c;
+}
+
+void* Node::staging_alloc(size_t bytes) {
+  const size_t c = stage_class(bytes ? bytes : 1);
+  {
+    std::lock_guard<std::mutex> lk(stage_mu_);
+    auto it = stage_pool_.find(c);
+    if (it != stage_pool_.end() && !it->second.empty()) {
+      void* p = it->second.back();
+      it->second.pop_back();
+      stage_pooled_bytes_ -= c;
+      return p;
+    }
+  }
+  DeviceGuard g(cfg_.device);
+  void* p = nullptr;
+  // portable + mapped: under unified addressing the host pointer is valid in kernels of every device of the process
+  if (cudaHostAlloc(&p, c, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void Node::staging_free(void* p, size_t bytes) {
+  if (!p) return;
+  const size_t c = stage_class(bytes ? bytes : 1);
+  {
+    std::lock_guard<std::mutex> lk(stage_mu_);
+    if (stage_pooled_bytes_ + c <= (size_t)cfg_.staging_pool_bytes) {
+      stage_pool_[c].push_back(p);
+      stage_pooled_bytes_ += c;
+      return;
+    }
+  }
+  cudaFreeHost(p);
+}
 
 bool Node::ensure_slot(Slot* s, const ModelDesc& d, int64_t rows, std::string* err) {
   int64_t cap_rows = rows > cfg_.max_batch ? rows : cfg_.max_batch;
@@ -576,14 +644,10 @@ bool Node::ensure_slot(Slot* s, const ModelDesc& d, int64_t rows, std::string* e
   size_t ws = model_ws_bytes(d);
   if (io > s->io_cap) {
     cudaStreamSynchronize(compute_);
-    if (s->h_in) cudaFreeHost(s->h_in);
-    if (s->h_out) cudaFreeHost(s->h_out);
     if (s->d_in) cudaFree(s->d_in);
     if (s->d_out) cudaFree(s->d_out);
-    s->h_in = s->h_out = s->d_in = s->d_out = nullptr;
+    s->d_in = s->d_out = nullptr;
     s->io_cap = 0;
-    CU_OK(cudaHostAlloc((void**)&s->h_in, io, cudaHostAllocPortable), err, false);
-    CU_OK(cudaHostAlloc((void**)&s->h_out, io, cudaHostAllocPortable), err, false);
     CU_OK(cudaMalloc((void**)&s->d_in, io), err, false);
     CU_OK(cudaMalloc((void**)&s->d_out, io), err, false);
     s->io_cap = io;
@@ -618,60 +682,111 @@ int Node::describe(const ModelId& id, ModelDesc* desc, int* outcome, std::string
   return 0;
 }
 
-int Node::predict_host(const ModelId& id, const void* x, int64_t n_elems, int in_dtype, const OutAllocFn& y_alloc,
-                       int* outcome, ModelDesc* desc_out, std::string* err) {
-  PredictRequest req;
-  int rc = fetch(id, &req.dm, err);  // handleModelRequest -> fetchModel, before any input validation (as the reference)
+int Node::prepare(const ModelId& id, int64_t n_elems, int in_dtype, PredictRequest* req, int* outcome, std::string* err) {
+  int rc = fetch(id, &req->dm, err);  // handleModelRequest -> fetchModel, before any input validation (as the reference)
   if (rc < 0) return rc;
   if (outcome) *outcome = rc;
+  const ModelDesc& d = req->dm->desc;
+  const int64_t per_row = d.tmpl == Template::Affine ? 1 : d.in_dim;
+  auto reject = [&](const std::string& msg) {
+    unpin(req->dm);
+    req->dm.reset();
+    *err = msg;
+    return TFSC_E_INVALID;
+  };
+  if (in_dtype != d.input_dtype)
+    return reject("input dtype " + std::to_string(in_dtype) + " does not match the model signature (expects dtype " +
+                  std::to_string(d.input_dtype) + ")");
+  if (n_elems <= 0 || n_elems % per_row != 0)
+    return reject("input has " + std::to_string(n_elems) + " elements; model " + id.name + " expects a multiple of " +
+                  std::to_string(per_row));
+  const int64_t rows = n_elems / per_row;
+  if (rows > cfg_.max_request_rows)
+    return reject("request has " + std::to_string(rows) + " rows; gpu.maxRequestRows is " + std::to_string(cfg_.max_request_rows));
+  req->rows = rows;
+  return 0;
+}
+
+void Node::abandon(PredictRequest* req) {
+  if (req->dm) {
+    unpin(req->dm);
+    req->dm.reset();
+  }
+}
+
+void Node::enqueue(PredictRequest* req) {
+  req->rc = 1;
+  req->arrival_ns = now_ns();
+  {
+    std::lock_guard<std::mutex> lk(q_mu_);
+    req->seq = ++seq_;
+    auto& q = pending_[req->dm.get()];
+    if (q.empty()) order_.insert({req->seq, req->dm.get()});
+    q.push_back(req);
+  }
+  q_cv_.notify_all();
+}
+
+// completion: release the model pin, then hand the result over. Nothing of `r` may be touched after the hand-over (a
+// synchronous caller destroys the request as soon as it sees rc != 1; on_done owns the request's lifetime).
+void Node::complete(PredictRequest* r, int rc, const std::string& err) {
+  std::shared_ptr<DeviceModel> dm = std::move(r->dm);
+  if (dm) unpin(dm);
+  if (r->on_done) {
+    r->err = err;
+    r->rc = rc;
+    auto fn = std::move(r->on_done);
+    fn(r);
+    return;
+  }
+  std::lock_guard<std::mutex> l(r->mu);
+  r->err = err;
+  r->rc = rc;
+  r->cv.notify_all();
+}
+
+int Node::predict_host(const ModelId& id, const void* x, int64_t n_elems, int in_dtype, const OutAllocFn& y_alloc,
+                       int* outcome, ModelDesc* desc_out, std::string* err, int64_t deadline_ns) {
+  PredictRequest req;
+  int rc = prepare(id, x ? n_elems : 0, in_dtype, &req, outcome, err);
+  if (rc < 0) return rc;
   const ModelDesc& d = req.dm->desc;
   if (desc_out) *desc_out = d;
-  const int64_t per_row = d.tmpl == Template::Affine ? 1 : d.in_dim;
-  if (in_dtype != d.input_dtype) {
-    unpin(req.dm);
-    *err = "input dtype " + std::to_string(in_dtype) + " does not match the model signature (expects dtype " +
-           std::to_string(d.input_dtype) + ")";
-    return TFSC_E_INVALID;
-  }
-  if (!x || n_elems <= 0 || n_elems % per_row != 0) {
-    unpin(req.dm);
-    *err = "input has " + std::to_string(n_elems) + " elements; model " + id.name + " expects a multiple of " +
-           std::to_string(per_row);
-    return TFSC_E_INVALID;
-  }
-  const int64_t rows = n_elems / per_row;
-  if (rows > cfg_.max_request_rows) {
-    unpin(req.dm);
-    *err = "request has " + std::to_string(rows) + " rows; gpu.maxRequestRows is " + std::to_string(cfg_.max_request_rows);
-    return TFSC_E_INVALID;
-  }
-  void* y = y_alloc(d, rows);
+  void* y = y_alloc(d, req.rows);
   if (!y) {
-    unpin(req.dm);
+    abandon(&req);
     *err = "output buffer too small";
     return TFSC_E_BUFFER;
   }
-  req.x = x;
-  req.y = y;
-  req.rows = rows;
-  {
-    std::lock_guard<std::mutex> lk(q_mu_);
-    req.seq = ++seq_;
-    auto& q = pending_[req.dm.get()];
-    if (q.empty()) order_.insert({req.seq, req.dm.get()});
-    q.push_back(&req);
+  // the client thread stages its own rows (pinned, device-accessible): the batcher thread never touches request payloads,
+  // the gather kernel pulls the rows over PCIe straight into the batch buffer
+  const size_t in_b = (size_t)req.rows * row_in_bytes(d), out_b = (size_t)req.rows * row_out_bytes(d);
+  const size_t in_al = (in_b + 255) & ~(size_t)255;
+  char* st = static_cast<char*>(staging_alloc(in_al + out_b));
+  if (!st) {
+    abandon(&req);
+    *err = "cannot pin " + std::to_string(in_al + out_b) + " bytes of request staging";
+    return TFSC_E_EXHAUSTED;
   }
-  q_cv_.notify_all();
+  memcpy(st, x, in_b);
+  req.x = st;
+  req.y = st + in_al;
+  req.host_staged = true;
+  req.deadline_ns = deadline_ns;
+  enqueue(&req);
   {
     std::unique_lock<std::mutex> lk(req.mu);
     req.cv.wait(lk, [&] { return req.rc != 1; });
   }
+  if (req.rc == 0) memcpy(y, st + in_al, out_b);
+  staging_free(st, in_al + out_b);
   if (req.rc < 0) *err = req.err;
   return req.rc;
 }
 
 void Node::batcher_loop() {
   cudaSetDevice(cfg_.device);
+  std::vector<CopySeg> segs;
   for (;;) {
     std::unique_lock<std::mutex> lk(q_mu_);
     q_cv_.wait(lk, [&] { return stop_ || !order_.empty(); });
@@ -682,12 +797,29 @@ void Node::batcher_loop() {
     // oldest-request-first: requests are served in arrival order, and every request of the same
     // model that is already queued rides along (up to gpu.maxBatch rows) in the same pass over W
     DeviceModel* m = order_.begin()->second;
-    order_.erase(order_.begin());
     auto& q = pending_[m];
-    std::vector<PredictRequest*> batch;
+    if (cfg_.tick_us > 0 && !stop_) {
+      // batching window (gpu.tickMicros): a partial batch waits for more rows until its oldest request is tick old
+      int64_t queued = 0;
+      for (auto* r : q) queued += r->rows;
+      const int64_t due = q.front()->arrival_ns + (int64_t)cfg_.tick_us * 1000;
+      const int64_t now = now_ns();
+      if (queued < cfg_.max_batch && now < due) {
+        q_cv_.wait_for(lk, std::chrono::nanoseconds(due - now));
+        continue;  // re-evaluate: more rows may have arrived, or another model is now the oldest
+      }
+    }
+    order_.erase(order_.begin());
+    std::vector<PredictRequest*> batch, expired;
     int64_t rows = 0;
+    const int64_t now = now_ns();
     while (!q.empty()) {
       PredictRequest* r = q.front();
+      if (r->deadline_ns > 0 && now > r->deadline_ns) {  // still queued past its deadline: never launched
+        expired.push_back(r);
+        q.pop_front();
+        continue;
+      }
       if (!batch.empty() && rows + r->rows > cfg_.max_batch) break;
       batch.push_back(r);
       rows += r->rows;
@@ -696,6 +828,12 @@ void Node::batcher_loop() {
     }
     if (!q.empty()) order_.insert({q.front()->seq, m});
     else pending_.erase(m);
+    if (!expired.empty()) {
+      lk.unlock();
+      for (auto* r : expired) complete(r, TFSC_E_TIMEOUT, "deadline exceeded while queued");
+      lk.lock();
+    }
+    if (batch.empty()) continue;
     Slot* s = nullptr;
     slot_cv_.wait(lk, [&] {
       for (auto& c : slots_)
@@ -706,12 +844,8 @@ void Node::batcher_loop() {
       return stop_;
     });
     if (!s) {  // shutting down
-      for (auto* r : batch) {
-        std::lock_guard<std::mutex> l(r->mu);
-        r->rc = TFSC_E_INTERNAL;
-        r->err = "server shutting down";
-        r->cv.notify_all();
-      }
+      lk.unlock();
+      for (auto* r : batch) complete(r, TFSC_E_INTERNAL, "server shutting down");
       continue;
     }
     s->busy = true;
@@ -724,23 +858,35 @@ void Node::batcher_loop() {
     if (!ensure_slot(s, d, rows, &err)) e = cudaErrorMemoryAllocation;
     const size_t rin = row_in_bytes(d), rout = row_out_bytes(d);
     if (e == cudaSuccess) {
+      // three streams: gather | kernels | scatter, chained by events, so the transfers of neighbouring batches overlap
+      // the weight-streaming kernels instead of serialising with them. Gather and scatter are one kernel each over a
+      // segment table (X6): sources / destinations are pinned host staging (PCIe), local HBM or peer windows (NVLink, X7).
+      segs.clear();
       size_t off = 0;
+      int64_t h2d = 0;
       for (auto* r : batch) {
-        memcpy(s->h_in + off, r->x, (size_t)r->rows * rin);
+        segs.push_back({r->x, s->d_in + off, (uint64_t)r->rows * rin});
+        if (r->host_staged) h2d += (int64_t)((size_t)r->rows * rin);
         off += (size_t)r->rows * rin;
       }
-      // three streams: inputs H2D | kernels | results D2H, chained by events, so the copies of
-      // neighbouring batches overlap the weight-streaming kernels instead of serialising with them
-      e = cudaMemcpyAsync(s->d_in, s->h_in, off, cudaMemcpyHostToDevice, in_);
-      h2d_inputs_ += (int64_t)off;
+      e = launch_copy_segments(segs.data(), (int)segs.size(), in_);
+      h2d_inputs_ += h2d;
       if (e == cudaSuccess) e = cudaEventRecord(s->in_done, in_);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(compute_, s->in_done, 0);
       if (e == cudaSuccess && !dm->ready_seen) e = cudaStreamWaitEvent(compute_, dm->ready, 0);
       if (e == cudaSuccess) e = run_model(*dm, s->d_in, rows, s->d_out, s->scratch, s->ws, s->ws_cap, compute_);
       if (e == cudaSuccess) e = cudaEventRecord(s->k_done, compute_);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(out_, s->k_done, 0);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(s->h_out, s->d_out, (size_t)rows * rout, cudaMemcpyDeviceToHost, out_);
-      d2h_outputs_ += (int64_t)rows * (int64_t)rout;
+      segs.clear();
+      off = 0;
+      int64_t d2h = 0;
+      for (auto* r : batch) {
+        segs.push_back({s->d_out + off, r->y, (uint64_t)r->rows * rout});
+        if (r->host_staged) d2h += (int64_t)((size_t)r->rows * rout);
+        off += (size_t)r->rows * rout;
+      }
+      if (e == cudaSuccess) e = launch_copy_segments(segs.data(), (int)segs.size(), out_);
+      d2h_outputs_ += d2h;
       if (e == cudaSuccess) e = cudaEventRecord(s->done, out_);
     }
     batches_++;
@@ -748,13 +894,9 @@ void Node::batcher_loop() {
     if (e != cudaSuccess) {
       if (err.empty()) err = std::string("launch failed: ") + cudaGetErrorString(e);
       cudaGetLastError();
-      for (auto* r : batch) {
-        unpin(r->dm);
-        std::lock_guard<std::mutex> l(r->mu);
-        r->rc = TFSC_E_INTERNAL;
-        r->err = err;
-        r->cv.notify_all();
-      }
+      cudaDeviceSynchronize();  // nothing of this batch may still write into the requests' buffers
+      cudaGetLastError();
+      for (auto* r : batch) complete(r, TFSC_E_INTERNAL, err);
       lk.lock();
       s->busy = false;
       lk.unlock();
@@ -768,6 +910,16 @@ void Node::batcher_loop() {
     lk.unlock();
     q_cv_.notify_all();
   }
+  // shutting down: whatever is still queued fails
+  std::vector<PredictRequest*> rest;
+  {
+    std::lock_guard<std::mutex> lk(q_mu_);
+    for (auto& kv : pending_)
+      for (auto* r : kv.second) rest.push_back(r);
+    pending_.clear();
+    order_.clear();
+  }
+  for (auto* r : rest) complete(r, TFSC_E_INTERNAL, "server shutting down");
 }
 
 void Node::completer_loop() {
@@ -776,38 +928,25 @@ void Node::completer_loop() {
     Slot* s = nullptr;
     {
       std::unique_lock<std::mutex> lk(q_mu_);
-      q_cv_.wait(lk, [&] { return !inflight_.empty() || (stop_ && order_.empty()); });
+      q_cv_.wait(lk, [&] { return !inflight_.empty() || batcher_done_; });
       if (inflight_.empty()) {
-        if (stop_) break;
+        if (batcher_done_) break;
         continue;
       }
       s = inflight_.front();
       inflight_.pop_front();
     }
     cudaError_t e = cudaEventSynchronize(s->done);
-    const size_t rout = row_out_bytes(s->dm->desc);
-    size_t off = 0;
-    for (auto* r : s->reqs) {
-      if (e == cudaSuccess) memcpy(r->y, s->h_out + off, (size_t)r->rows * rout);
-      off += (size_t)r->rows * rout;
-    }
-    for (auto* r : s->reqs) {
-      std::shared_ptr<DeviceModel> dm = r->dm;
-      {
-        std::lock_guard<std::mutex> l(r->mu);
-        r->rc = e == cudaSuccess ? 0 : TFSC_E_INTERNAL;
-        if (e != cudaSuccess) r->err = std::string("execution failed: ") + cudaGetErrorString(e);
-        r->cv.notify_all();
-      }
-      unpin(dm);
-    }
+    const std::string msg = e == cudaSuccess ? std::string() : std::string("execution failed: ") + cudaGetErrorString(e);
+    std::vector<PredictRequest*> reqs = std::move(s->reqs);
     s->reqs.clear();
     s->dm.reset();
     {
       std::lock_guard<std::mutex> lk(q_mu_);
-      s->busy = false;
+      s->busy = false;  // the slot's device buffers are free again (results already sit in the requests' own buffers)
     }
     slot_cv_.notify_all();
+    for (auto* r : reqs) complete(r, e == cudaSuccess ? 0 : TFSC_E_INTERNAL, msg);
   }
 }
 

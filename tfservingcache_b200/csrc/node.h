@@ -49,18 +49,28 @@ struct NodeConfig {
   int max_request_rows = 1024;      // largest single request
   double fetch_timeout_s = 10.0;    // ModelFetchTimeout (main.go:122)
   int slots = 4;                    // staging slots in flight
+  int tick_us = 0;                  // gpu.tickMicros: hold a partial batch up to this long for more rows (0 = launch at once)
+  int64_t staging_pool_bytes = (int64_t)2 << 30;  // pinned request-staging buffers kept for reuse
 };
 
-struct PredictRequest {  // one caller blocked in tfsc_predict
+// One Predict request inside the node. `x` / `y` are DEVICE-ACCESSIBLE addresses: a pinned host staging buffer (host
+// callers: the client thread copied its rows there, the gather kernel reads them over PCIe), local HBM, or a peer GPU's
+// forward window (requests forwarded by another rank, a6: read / written over NVLink). Completion is a condition variable
+// (synchronous callers) or the `on_done` callback (tickets, forwarded requests).
+struct PredictRequest {
   std::shared_ptr<DeviceModel> dm;
   const void* x = nullptr;
   void* y = nullptr;
   int64_t rows = 0;
-  uint64_t seq = 0;  // global arrival order (the batcher serves oldest-request-first)
-  int rc = 1;  // 1 = pending
+  bool host_staged = true;   // x / y are pinned host memory (h2d / d2h byte counters), else device / peer memory
+  uint64_t seq = 0;          // global arrival order (the batcher serves oldest-request-first)
+  int64_t arrival_ns = 0;    // steady clock
+  int64_t deadline_ns = 0;   // steady clock (CLOCK_MONOTONIC); 0 = none. Checked while the request is still queued
+  int rc = 1;                // 1 = pending
   std::string err;
   std::mutex mu;
   std::condition_variable cv;
+  std::function<void(PredictRequest*)> on_done;  // if set: called once (completer / batcher thread) instead of the notify
 };
 
 class Node {
@@ -82,7 +92,20 @@ class Node {
   // buffer once the model is known (return nullptr to reject, e.g. caller buffer too small).
   using OutAllocFn = std::function<void*(const ModelDesc&, int64_t rows)>;
   int predict_host(const ModelId& id, const void* x, int64_t n_elems, int in_dtype, const OutAllocFn& y_alloc, int* outcome,
-                   ModelDesc* desc_out, std::string* err);
+                   ModelDesc* desc_out, std::string* err, int64_t deadline_ns = 0);
+  // The two halves of predict_host for asynchronous callers (tickets, forwarded requests):
+  // prepare = fetchModel + signature checks, fills req->dm (pinned) and req->rows; on error nothing stays pinned.
+  int prepare(const ModelId& id, int64_t n_elems, int in_dtype, PredictRequest* req, int* outcome, std::string* err);
+  // enqueue = hand the request to the batcher; req->x / req->y must be set and the request must stay alive until it
+  // completes (rc != 1 / on_done called). The pin taken by prepare() is released on completion.
+  void enqueue(PredictRequest* req);
+  void abandon(PredictRequest* req);  // after a successful prepare() that will not be enqueued: drop the pin
+  // pinned, device-accessible request staging (size-class pool); nullptr when the host cannot pin more memory
+  void* staging_alloc(size_t bytes);
+  void staging_free(void* p, size_t bytes);
+  static size_t row_in_bytes(const ModelDesc& d);
+  static size_t row_out_bytes(const ModelDesc& d);
+  static int64_t now_ns();
   // describe a model (triggers fetch): needed to size outputs before predict
   int describe(const ModelId& id, ModelDesc* desc, int* outcome, std::string* err);
   // device-buffer predict on `stream` (nullptr = compute stream), asynchronous
@@ -90,10 +113,13 @@ class Node {
   int sync();
   void stats(tfsc_stats* s);
   int device() const { return cfg_.device; }
+  // serving.maxConcurrentModels at run time (the reference re-reads viper keys per call, cluster.go:117): the resident
+  // prefix shrinks at once (models beyond it are unloaded) and grows with the following reloads
+  void set_max_concurrent_models(int n);
 
  private:
   struct Slot {
-    char *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *scratch = nullptr;
+    char *d_in = nullptr, *d_out = nullptr, *scratch = nullptr;
     void* ws = nullptr;
     size_t io_cap = 0, scratch_cap = 0, ws_cap = 0;
     cudaEvent_t in_done = nullptr, k_done = nullptr, done = nullptr;
@@ -125,6 +151,7 @@ class Node {
   static size_t model_ws_bytes(const ModelDesc& d);
   void batcher_loop();
   void completer_loop();
+  void complete(PredictRequest* r, int rc, const std::string& err);
   cudaEvent_t get_event();
   void put_event(cudaEvent_t e);
 
@@ -154,6 +181,10 @@ class Node {
   // pinned block pool (exact-size reuse)
   std::mutex pool_mu_;
   std::unordered_map<size_t, std::vector<void*>> pool_;
+  // pinned request staging, power-of-two size classes
+  std::mutex stage_mu_;
+  std::unordered_map<size_t, std::vector<void*>> stage_pool_;
+  size_t stage_pooled_bytes_ = 0;
 
   // batcher
   std::mutex q_mu_;
@@ -164,7 +195,7 @@ class Node {
   std::deque<Slot*> inflight_;
   std::vector<Slot> slots_;
   std::thread batcher_, completer_;
-  bool stop_ = false;
+  bool stop_ = false, batcher_done_ = false;
 
   // stats (guarded by mu_ unless atomic)
   int64_t total_ = 0, hits_ = 0, misses_ = 0, ev_host_ = 0, ev_hbm_ = 0, h2d_weights_ = 0;

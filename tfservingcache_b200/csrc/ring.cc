@@ -129,6 +129,10 @@ bool ReplicaPicker::note_and_is_hot(const std::string& key, int members) {
 int ReplicaPicker::pick(const std::string& key, int n_replicas, int members) {
   if (n_replicas <= 1 || policy_ == "first") return 0;
   if (policy_ == "random") return (int)(next() % (uint64_t)n_replicas);
+  if (policy_ == "hash") {  // stateless: every process picks the same replica for a key without sharing any state
+    const std::string k2 = key + "\x01replica";
+    return (int)(crc32_ieee(k2.data(), k2.size()) % (uint32_t)n_replicas);
+  }
   return note_and_is_hot(key, members) ? (int)(next() % (uint64_t)n_replicas) : 0;
 }
 
@@ -192,7 +196,7 @@ int tfsc_ring_getn(const tfsc_ring* r, const char* key, int n, char* buf, size_t
 }
 tfsc_picker* tfsc_picker_new(const char* policy, uint64_t seed, double hot_fraction) {
   std::string p = policy ? policy : "random";
-  if (p != "random" && p != "first" && p != "hot-spread" && p != "balanced") {
+  if (p != "random" && p != "first" && p != "hot-spread" && p != "balanced" && p != "hash") {
     tfsc::fail(TFSC_E_INVALID, "unknown proxy.replicaPick '%s'", p.c_str());
     return nullptr;
   }

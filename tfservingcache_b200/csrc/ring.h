@@ -40,6 +40,9 @@ class Ring {
 //                models (paging a 1 GB model over PCIe costs ~100x serving it) and k copies of the few hot
 //                ones. Deterministic given the seed and the request sequence, so independent processes
 //                that see the same stream agree without communicating.
+//   "hash"       replica index = crc32(key + "\x01replica") mod k: stateless, so every process (one rank per GPU, requests
+//                entering anywhere) sends a key to the same replica and a model is cached once, yet keys spread over
+//                all k candidates of the ring.
 //   "balanced"   hot-spread + sticky power-of-two-choices: the first request of a cold key binds it to the
 //                candidate replica that currently holds the fewest keys (the 20-vnode ring alone is +-16 %
 //                uneven in keys per member; every resident model costs one pass over its weights per tick).

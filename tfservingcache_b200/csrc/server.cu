@@ -12,6 +12,7 @@
 #include <new>
 #include <stdexcept>
 
+#include "forward.h"
 #include "json.h"
 #include "kernels.h"
 #include "node.h"
@@ -30,14 +31,17 @@ struct tfsc_server {
   std::mutex ring_mu;
   Ring ring;
   std::map<std::string, int> member_node;
+  std::vector<std::string> member_list;    // current members in the order given (index = member id of tfsc_predict_member)
+  std::map<std::string, int> member_rank;  // member string -> rank of the process that serves it (cluster.endpoints index)
   int replicas = 1;
   std::mutex pick_mu;
   std::unique_ptr<ReplicaPicker> picker;
   std::atomic<int64_t> req_rest{0}, req_grpc{0}, fail_rest{0}, fail_grpc{0};
+  std::unique_ptr<Forwarder> fwd;  // declared last: destroyed first (it hands requests to nodes[0])
 };
 
 static int route(tfsc_server* s, const std::string& name, const std::string& version, std::vector<int>* nodes,
-                 int* picked) {
+                 int* picked, std::vector<int>* ranks = nullptr) {
   std::vector<std::string> members;
   const std::string key = name + "##" + version;
   int n_members = 0;
@@ -50,6 +54,10 @@ static int route(tfsc_server* s, const std::string& name, const std::string& ver
     for (auto& m : members) {
       auto it = s->member_node.find(m);
       nodes->push_back(it == s->member_node.end() ? -1 : it->second);
+      if (ranks) {
+        auto rt = s->member_rank.find(m);
+        ranks->push_back(rt == s->member_rank.end() ? -1 : rt->second);
+      }
     }
   }
   // "Pick random node", taskhandler.go:91 (policy "random"), or the primary / hot-spread / balanced variants
@@ -63,8 +71,14 @@ static int route(tfsc_server* s, const std::string& name, const std::string& ver
 static void set_members(tfsc_server* s, const std::vector<std::string>& members) {
   std::lock_guard<std::mutex> lk(s->ring_mu);
   s->ring.set(members);
+  s->member_list = members;
   s->member_node.clear();
   for (size_t i = 0; i < s->local_members.size(); ++i) s->member_node[s->local_members[i]] = (int)i;
+  // with cluster.endpoints the i-th member is served by the process listening on endpoints[i] (one rank per GPU)
+  s->member_rank.clear();
+  if (s->fwd)
+    for (size_t i = 0; i < members.size() && (int)i < s->fwd->world(); ++i)
+      if (!s->member_node.count(members[i])) s->member_rank[members[i]] = (int)i;
 }
 
 // No exception may cross the C ABI (a cgo / ctypes caller would see std::terminate): allocation failures and
@@ -135,7 +149,7 @@ static tfsc_server* server_create_impl(const char* config_json) {
   }
   s->replicas = (int)std::max(s->cfg.get_num("proxy.replicasPerModel", 1), 1.0);
   const std::string policy = s->cfg.get_str("proxy.replicaPick", "random");
-  if (policy != "random" && policy != "first" && policy != "hot-spread" && policy != "balanced") {
+  if (policy != "random" && policy != "first" && policy != "hot-spread" && policy != "balanced" && policy != "hash") {
     fail(TFSC_E_INVALID, "unknown proxy.replicaPick '%s'", policy.c_str());
     return nullptr;
   }
@@ -156,6 +170,7 @@ static tfsc_server* server_create_impl(const char* config_json) {
     nc.max_request_rows = (int)s->cfg.get_int("gpu.maxRequestRows", 1024);
     nc.fetch_timeout_s = s->cfg.get_num("serving.modelFetchTimeout", 10.0);
     nc.slots = (int)s->cfg.get_int("gpu.stagingSlots", 4);
+    nc.tick_us = (int)s->cfg.get_int("gpu.tickMicros", 0);
     auto node = std::make_unique<Node>(nc, s->provider.get());
     if (!node->init(&err)) {
       fail(TFSC_E_NO_DEVICE, "node %zu (device %d): %s", i, devices[i], err.c_str());
@@ -181,6 +196,26 @@ static tfsc_server* server_create_impl(const char* config_json) {
   if (const Json* m = s->cfg.get("gpu.members"))
     for (auto& v : m->arr) members.push_back(v.string());
   if (members.empty()) members = s->local_members;
+  if (const Json* eps = s->cfg.get("cluster.endpoints")) {
+    // one process per GPU: requests whose ring owner is another rank are forwarded there (a6), tensors over NVLink
+    FwdConfig fc;
+    for (auto& v : eps->arr) fc.endpoints.push_back(v.string());
+    fc.rank = (int)s->cfg.get_int("cluster.rank", 0);
+    fc.slot_bytes = (size_t)s->cfg.get_int("cluster.slotBytes", 1 << 20);
+    fc.slots = (int)s->cfg.get_int("cluster.windowSlots", 128);
+    fc.timeout_s = s->cfg.get_num("proxy.grpcTimeout", 10.0);
+    fc.workers = (int)s->cfg.get_int("cluster.forwardWorkers", 8);
+    if (fc.endpoints.size() != members.size()) {
+      fail(TFSC_E_INVALID, "cluster.endpoints must list one endpoint per entry of gpu.members (%zu vs %zu)", fc.endpoints.size(),
+           members.size());
+      return nullptr;
+    }
+    s->fwd = std::make_unique<Forwarder>(fc, s->nodes[0].get());
+    if (!s->fwd->init(&err)) {
+      fail(TFSC_E_INVALID, "%s", err.c_str());
+      return nullptr;
+    }
+  }
   set_members(s.get(), members);
   return s.release();
 }
@@ -205,6 +240,15 @@ int tfsc_route(tfsc_server* s, const char* model_name, const char* version, int*
   for (int i = 0; i < rc && i < cap; ++i) nodes[i] = v[i];
   if (picked) *picked = p;
   return rc;
+}
+
+static int check_device_early() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(TFSC_E_NO_DEVICE, "no CUDA device available: this library has no CPU fallback");
+  }
+  return 0;
 }
 
 static Node* node_at(tfsc_server* s, int node) {
@@ -263,21 +307,35 @@ int tfsc_host_list(tfsc_server* s, int node, char* buf, size_t cap) {
   return c;
 }
 
-// route -> parse version -> owner node. Shared by the three Predict entry points.
-static int resolve(tfsc_server* s, const std::string& name, const std::string& version, Node** node, ModelId* id) {
-  std::vector<int> nodes;
+// route -> parse version -> owner. The owner is a node of this process (*node) or another rank (*remote >= 0, a6).
+// Shared by the three Predict entry points.
+static int resolve(tfsc_server* s, const std::string& name, const std::string& version, Node** node, ModelId* id,
+                   int* remote = nullptr) {
+  std::vector<int> nodes, ranks;
   int picked = 0;
-  int rc = route(s, name, version, &nodes, &picked);
+  int rc = route(s, name, version, &nodes, &picked, &ranks);
   if (rc < 0) return rc;
   int local = nodes[picked];
-  if (local < 0)
-    return fail(TFSC_E_NOT_FOUND, "owner of %s##%s is not a GPU of this process", name.c_str(), version.c_str());
+  if (remote) *remote = -1;
+  if (local < 0) {
+    if (!remote || ranks[picked] < 0)
+      return fail(TFSC_E_NOT_FOUND, "owner of %s##%s is not a GPU of this process", name.c_str(), version.c_str());
+    *remote = ranks[picked];
+  }
   int64_t v;
   if (!parse_int64(version, &v))  // handleModelRequest, cachemanager.go:297
     return fail(TFSC_E_INVALID, "strconv.ParseInt: parsing \"%s\": invalid syntax", version.c_str());
-  *node = s->nodes[local].get();
+  *node = local >= 0 ? s->nodes[local].get() : nullptr;
   *id = {name, v};
   return 0;
+}
+
+// ensure-resident -> predict on the owner: a node of this process, or another rank through the forward hop
+// (taskhandler.go:95-147: the request goes to whichever node the ring names, tensors stay in device memory here)
+static int run_predict(tfsc_server* s, Node* node, int remote, const ModelId& id, const void* x, int64_t n, int dtype,
+                       const Node::OutAllocFn& alloc, std::string* err, int64_t deadline_ns = 0) {
+  if (node) return node->predict_host(id, x, n, dtype, alloc, nullptr, nullptr, err, deadline_ns);
+  return s->fwd->forward(remote, id.name, id.version, x, n, dtype, alloc, nullptr, deadline_ns, err);
 }
 
 // Output shape of a request with input shape `in_shape` that the executor will run as `rows` rows. Returns false (with
@@ -323,13 +381,36 @@ static bool out_shape(const ModelDesc& d, int64_t rows, const std::vector<int64_
   return true;
 }
 
+// owner = member `member` of the current member list (the cache tier of that member, cachemanager.ServeRest/ServeGrpc: no
+// ring lookup -- the caller already routed, e.g. with tfsc_route), local node or another rank
+static int resolve_member(tfsc_server* s, int member, const std::string& name, const std::string& version, Node** node,
+                          ModelId* id, int* remote) {
+  std::string m;
+  {
+    std::lock_guard<std::mutex> lk(s->ring_mu);
+    if (member < 0 || member >= (int)s->member_list.size()) return fail(TFSC_E_INVALID, "member index %d out of range", member);
+    m = s->member_list[member];
+    auto it = s->member_node.find(m);
+    *node = it == s->member_node.end() ? nullptr : s->nodes[it->second].get();
+    auto rt = s->member_rank.find(m);
+    *remote = rt == s->member_rank.end() ? -1 : rt->second;
+  }
+  if (!*node && *remote < 0) return fail(TFSC_E_NOT_FOUND, "member %s is not served by this process and has no cluster endpoint", m.c_str());
+  int64_t v;
+  if (!parse_int64(version, &v)) return fail(TFSC_E_INVALID, "strconv.ParseInt: parsing \"%s\": invalid syntax", version.c_str());
+  *id = {name, v};
+  return 0;
+}
+
 static int predict_impl(tfsc_server* s, const char* model_name, const char* version, const tfsc_tensor* in, int n_in,
-                        tfsc_tensor* out, int n_out) {
+                        tfsc_tensor* out, int n_out, int64_t deadline_ns, int member = -1) {
   if (!s || !model_name || !version || !in || n_in < 1 || !out || n_out < 1)
     return fail(TFSC_E_INVALID, "predict: bad arguments");
   Node* node;
   ModelId id;
-  int rc = resolve(s, model_name, version, &node, &id);
+  int remote = -1;
+  int rc = member >= 0 ? resolve_member(s, member, model_name, version, &node, &id, &remote)
+                       : resolve(s, model_name, version, &node, &id, &remote);
   if (rc < 0) return rc;
   const tfsc_tensor& x = in[0];
   if (n_in != 1) return fail(TFSC_E_INVALID, "predict: the model templates take exactly one input tensor (got %d)", n_in);
@@ -360,7 +441,7 @@ static int predict_impl(tfsc_server* s, const char* model_name, const char* vers
     o->nbytes = (size_t)on * 4;
     return o->data;
   };
-  rc = node->predict_host(id, x.data, n, x.dtype, alloc, nullptr, nullptr, &err);
+  rc = run_predict(s, node, remote, id, x.data, n, x.dtype, alloc, &err, deadline_ns);
   if (rc < 0 && !bad.empty()) return fail(TFSC_E_INVALID, "%s", bad.c_str());
   if (rc < 0) return fail(rc, "%s", err.c_str());
   return 0;
@@ -379,14 +460,15 @@ static int grpc_predict_impl(tfsc_server* s, const void* req, size_t req_len, vo
   const std::string version = std::to_string(view.version);
   Node* node;
   ModelId id;
-  int rc = resolve(s, view.model_name, version, &node, &id);
+  int remote = -1;
+  int rc = resolve(s, view.model_name, version, &node, &id, &remote);
   if (rc < 0) {
     s->fail_grpc++;
     return rc;
   }
   if (view.inputs.empty()) {
-    // the reference forwards even an empty request; residency is still ensured first
-    rc = node->fetch(id, nullptr, &err);
+    // the reference forwards even an empty request; residency is still ensured first (on the owner, when it is local)
+    rc = node ? node->fetch(id, nullptr, &err) : 0;
     s->fail_grpc++;
     if (rc < 0) return fail(rc, "%s", err.c_str());
     return fail(TFSC_E_INVALID, "PredictRequest has no inputs");
@@ -430,12 +512,12 @@ static int grpc_predict_impl(tfsc_server* s, const void* req, size_t req_len, vo
   };
   if (!input_ok) {
     std::string e2;
-    rc = node->fetch(id, nullptr, &e2);  // residency first, like the reference; then reject the tensor
+    rc = node ? node->fetch(id, nullptr, &e2) : 0;  // residency first, like the reference; then reject the tensor
     s->fail_grpc++;
     if (rc < 0) return fail(rc, "%s", e2.c_str());
     return fail(TFSC_E_INVALID, "%s", err.c_str());
   }
-  rc = node->predict_host(id, xdata, n, tv.dtype == TFSC_DT_INT32 ? TFSC_DT_INT32 : TFSC_DT_FLOAT, alloc, nullptr, nullptr, &err);
+  rc = run_predict(s, node, remote, id, xdata, n, tv.dtype == TFSC_DT_INT32 ? TFSC_DT_INT32 : TFSC_DT_FLOAT, alloc, &err);
   if (rc < 0) {
     free(buf);
     s->fail_grpc++;
@@ -542,7 +624,8 @@ static int rest_handle_impl(tfsc_server* s, const char* method, const char* url,
   if (qpos != std::string::npos) tail.resize(qpos);
   Node* node;
   ModelId id;
-  int rc = resolve(s, name, version, &node, &id);
+  int remote = -1;
+  int rc = resolve(s, name, version, &node, &id, &remote);
   auto fail_http = [&](int code, const std::string& msg) {
     s->fail_rest++;
     *http_status = code;
@@ -552,6 +635,9 @@ static int rest_handle_impl(tfsc_server* s, const char* method, const char* url,
   if (rc < 0) return fail_http(http_for(rc), tfsc_last_error());
   std::string err;
   const std::string m(method);
+  if (!node && !(m == "POST" && tail == ":predict"))
+    // only Predict takes the forward hop; status / metadata of a model are answered by the rank that owns it
+    return fail_http(404, "model " + name + " is owned by rank " + std::to_string(remote) + "; ask that rank for " + tail);
   if (m == "GET" && (tail.empty() || tail == "/")) {
     // the request passes through handleModelRequest (fetchModel) before TF-Serving answers
     rc = node->fetch(id, nullptr, &err);
@@ -607,7 +693,7 @@ static int rest_handle_impl(tfsc_server* s, const char* method, const char* url,
     }
     if (!ok || flat.empty()) {
       std::string e2;
-      rc = node->fetch(id, nullptr, &e2);  // residency is ensured before the body is looked at
+      rc = node ? node->fetch(id, nullptr, &e2) : 0;  // residency is ensured before the body is looked at
       if (rc < 0) return fail_http(http_for(rc), e2);
       return fail_http(400, err.empty() ? "empty request" : err);
     }
@@ -625,13 +711,13 @@ static int rest_handle_impl(tfsc_server* s, const char* method, const char* url,
       y.resize((size_t)on);
       return y.data();
     };
-    rc = node->predict_host(id, flat.data(), (int64_t)flat.size(), TFSC_DT_FLOAT, alloc, nullptr, nullptr, &err);
+    rc = run_predict(s, node, remote, id, flat.data(), (int64_t)flat.size(), TFSC_DT_FLOAT, alloc, &err);
     if (rc == TFSC_E_INVALID && err.find("input dtype") == 0) {
       // JSON numbers carry no dtype: the signature wants int32 (token ids) -> resend the same values as integers
       std::vector<int32_t> ints(flat.size());
       for (size_t i = 0; i < flat.size(); ++i) ints[i] = (int32_t)llround((double)flat[i]);
       err.clear();
-      rc = node->predict_host(id, ints.data(), (int64_t)ints.size(), TFSC_DT_INT32, alloc, nullptr, nullptr, &err);
+      rc = run_predict(s, node, remote, id, ints.data(), (int64_t)ints.size(), TFSC_DT_INT32, alloc, &err);
     }
     if (rc < 0) return fail_http(bad_sig.empty() ? http_for(rc) : 400, bad_sig.empty() ? err : bad_sig);
     // TF-Serving's writer: 4-space indent, arrays on one line, closing bracket on its own line
@@ -690,14 +776,216 @@ tfsc_server* tfsc_server_create(const char* config_json) {
 }
 int tfsc_predict(tfsc_server* s, const char* model_name, const char* version, const tfsc_tensor* in, int n_in,
                  tfsc_tensor* out, int n_out) {
-  return guarded("predict", [&] { return predict_impl(s, model_name, version, in, n_in, out, n_out); });
+  return guarded("predict", [&] { return predict_impl(s, model_name, version, in, n_in, out, n_out, 0); });
 }
+int tfsc_predict_deadline(tfsc_server* s, const char* model_name, const char* version, const tfsc_tensor* in, int n_in,
+                          tfsc_tensor* out, int n_out, int64_t deadline_ns) {
+  return guarded("predict", [&] { return predict_impl(s, model_name, version, in, n_in, out, n_out, deadline_ns); });
+}
+int tfsc_predict_member(tfsc_server* s, int member, const char* model_name, const char* version, const tfsc_tensor* in, int n_in,
+                        tfsc_tensor* out, int n_out, int64_t deadline_ns) {
+  return guarded("predict", [&] { return predict_impl(s, model_name, version, in, n_in, out, n_out, deadline_ns, member); });
+}
+int64_t tfsc_now_ns(void) { return Node::now_ns(); }
 int tfsc_grpc_predict(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len) {
   return guarded("grpc_predict", [&] { return grpc_predict_impl(s, req, req_len, resp, resp_len); });
 }
 int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const void* body, size_t body_len,
                      int* http_status, void** resp, size_t* resp_len) {
   return guarded("rest_handle", [&] { return rest_handle_impl(s, method, url, body, body_len, http_status, resp, resp_len); });
+}
+
+// ---- asynchronous Predict (tfsc_predict_submit / _wait / _release): a cgo handler does not park an OS
+// thread per in-flight request. submit = route + ensure-resident + signature checks + staging of the input rows (the
+// caller's input buffer is free again when submit returns); the output buffer is written by wait().
+struct tfsc_ticket {
+  tfsc_server* srv = nullptr;
+  Node* node = nullptr;
+  PredictRequest req;
+  char* staging = nullptr;
+  size_t staging_bytes = 0, in_al = 0, out_bytes = 0;
+  tfsc_tensor* out = nullptr;
+  std::vector<int64_t> oshape;
+  // requests owned by another rank take the (synchronous) forward hop on a helper thread
+  std::thread remote_thread;
+  std::mutex mu;
+  std::condition_variable cv;
+  int remote_rc = 1;
+  std::string remote_err;
+  std::vector<char> remote_x;
+  bool delivered = false;
+};
+
+static int submit_impl(tfsc_server* s, const char* model_name, const char* version, const tfsc_tensor* in, int n_in,
+                       tfsc_tensor* out, int n_out, int64_t deadline_ns, tfsc_ticket** ticket) {
+  if (!s || !model_name || !version || !in || n_in < 1 || !out || n_out < 1 || !ticket)
+    return fail(TFSC_E_INVALID, "predict_submit: bad arguments");
+  *ticket = nullptr;
+  Node* node;
+  ModelId id;
+  int remote = -1;
+  int rc = resolve(s, model_name, version, &node, &id, &remote);
+  if (rc < 0) return rc;
+  const tfsc_tensor& x = in[0];
+  if (n_in != 1) return fail(TFSC_E_INVALID, "predict: the model templates take exactly one input tensor (got %d)", n_in);
+  if ((x.dtype != TFSC_DT_FLOAT && x.dtype != TFSC_DT_INT32) || x.rank < 0 || x.rank > 8)
+    return fail(TFSC_E_INVALID, "predict: input must be DT_FLOAT or DT_INT32, rank <= 8");
+  int64_t n = 1;
+  std::vector<int64_t> ishape(x.shape, x.shape + x.rank);
+  for (auto d : ishape) {
+    if (d < 0 || (d != 0 && n > ((int64_t)1 << 40) / d)) return fail(TFSC_E_INVALID, "predict: bad input shape");
+    n *= d;
+  }
+  if ((size_t)n * 4 != x.nbytes || !x.data) return fail(TFSC_E_INVALID, "predict: input nbytes does not match shape");
+  auto t = std::make_unique<tfsc_ticket>();
+  t->srv = s;
+  t->node = node;
+  t->out = &out[0];
+  std::string err;
+  if (!node) {
+    // another rank owns the model: the forward hop is synchronous, run it beside the caller
+    t->remote_x.assign((const char*)x.data, (const char*)x.data + x.nbytes);
+    tfsc_ticket* tp = t.get();
+    const int dtype = x.dtype;
+    const std::string xname = x.name ? x.name : "";
+    const bool has_name = x.name != nullptr;
+    t->remote_thread = std::thread([tp, s, remote, id, n, dtype, ishape, xname, has_name, deadline_ns] {
+      std::string e2, bad;
+      auto alloc = [&](const ModelDesc& d, int64_t rows) -> void* {
+        if (has_name && d.input_name != xname) {
+          bad = "input '" + xname + "' does not match the model signature (expects '" + d.input_name + "')";
+          return nullptr;
+        }
+        if (!out_shape(d, rows, ishape, &tp->oshape, &bad)) return nullptr;
+        int64_t on = 1;
+        for (auto v : tp->oshape) on *= v;
+        if (!tp->out->data || tp->out->nbytes < (size_t)on * 4 || tp->oshape.size() > 8) return nullptr;
+        tp->out_bytes = (size_t)on * 4;
+        return tp->out->data;
+      };
+      int r = s->fwd->forward(remote, id.name, id.version, tp->remote_x.data(), n, dtype, alloc, nullptr, deadline_ns, &e2);
+      std::lock_guard<std::mutex> lk(tp->mu);
+      tp->remote_rc = r < 0 && !bad.empty() ? TFSC_E_INVALID : r;
+      tp->remote_err = !bad.empty() ? bad : e2;
+      tp->cv.notify_all();
+    });
+    *ticket = t.release();
+    return 0;
+  }
+  rc = node->prepare(id, n, x.dtype, &t->req, nullptr, &err);
+  if (rc < 0) return fail(rc, "%s", err.c_str());
+  const ModelDesc& d = t->req.dm->desc;
+  std::string bad;
+  if (x.name && d.input_name != x.name)
+    bad = "input '" + std::string(x.name) + "' does not match the model signature (expects '" + d.input_name + "')";
+  if (bad.empty()) out_shape(d, t->req.rows, ishape, &t->oshape, &bad);
+  if (!bad.empty()) {
+    node->abandon(&t->req);
+    return fail(TFSC_E_INVALID, "%s", bad.c_str());
+  }
+  int64_t on = 1;
+  for (auto v : t->oshape) on *= v;
+  t->out_bytes = (size_t)on * 4;
+  if (!out[0].data || out[0].nbytes < t->out_bytes || t->oshape.size() > 8) {
+    node->abandon(&t->req);
+    return fail(TFSC_E_BUFFER, "output buffer too small");
+  }
+  t->in_al = (x.nbytes + 255) & ~(size_t)255;
+  t->staging_bytes = t->in_al + t->out_bytes;
+  t->staging = static_cast<char*>(node->staging_alloc(t->staging_bytes));
+  if (!t->staging) {
+    node->abandon(&t->req);
+    return fail(TFSC_E_EXHAUSTED, "cannot pin %zu bytes of request staging", t->staging_bytes);
+  }
+  memcpy(t->staging, x.data, x.nbytes);
+  t->req.x = t->staging;
+  t->req.y = t->staging + t->in_al;
+  t->req.host_staged = true;
+  t->req.deadline_ns = deadline_ns;
+  node->enqueue(&t->req);
+  *ticket = t.release();
+  return 0;
+}
+
+static int wait_impl(tfsc_ticket* t, int64_t timeout_ns) {
+  if (!t) return fail(TFSC_E_INVALID, "predict_wait: null ticket");
+  int rc;
+  std::string err;
+  if (!t->node) {
+    std::unique_lock<std::mutex> lk(t->mu);
+    auto pred = [&] { return t->remote_rc != 1; };
+    if (timeout_ns < 0) t->cv.wait(lk, pred);
+    else if (!t->cv.wait_for(lk, std::chrono::nanoseconds(timeout_ns), pred))
+      return fail(TFSC_E_TIMEOUT, "predict_wait: request still in flight");
+    rc = t->remote_rc;
+    err = t->remote_err;
+  } else {
+    std::unique_lock<std::mutex> lk(t->req.mu);
+    auto pred = [&] { return t->req.rc != 1; };
+    if (timeout_ns < 0) t->req.cv.wait(lk, pred);
+    else if (!t->req.cv.wait_for(lk, std::chrono::nanoseconds(timeout_ns), pred))
+      return fail(TFSC_E_TIMEOUT, "predict_wait: request still in flight");
+    rc = t->req.rc;
+    err = t->req.err;
+    if (rc == 0 && !t->delivered) memcpy(t->out->data, t->staging + t->in_al, t->out_bytes);
+  }
+  if (rc < 0) return fail(rc, "%s", err.c_str());
+  if (!t->delivered) {
+    t->out->dtype = TFSC_DT_FLOAT;
+    t->out->rank = (int32_t)t->oshape.size();
+    for (size_t i = 0; i < t->oshape.size(); ++i) t->out->shape[i] = t->oshape[i];
+    t->out->nbytes = t->out_bytes;
+    t->delivered = true;
+  }
+  return 0;
+}
+
+int tfsc_predict_submit(tfsc_server* s, const char* model_name, const char* version, const tfsc_tensor* in, int n_in,
+                        tfsc_tensor* out, int n_out, int64_t deadline_ns, tfsc_ticket** ticket) {
+  return guarded("predict_submit", [&] { return submit_impl(s, model_name, version, in, n_in, out, n_out, deadline_ns, ticket); });
+}
+int tfsc_predict_wait(tfsc_ticket* t, int64_t timeout_ns) {
+  return guarded("predict_wait", [&] { return wait_impl(t, timeout_ns); });
+}
+void tfsc_predict_release(tfsc_ticket* t) {
+  if (!t) return;
+  if (t->node) {
+    {  // the batcher / kernels may still use the staging buffer: wait for the request to retire
+      std::unique_lock<std::mutex> lk(t->req.mu);
+      t->req.cv.wait(lk, [&] { return t->req.rc != 1; });
+    }
+    t->node->staging_free(t->staging, t->staging_bytes);
+  } else if (t->remote_thread.joinable()) {
+    t->remote_thread.join();
+  }
+  delete t;
+}
+
+// ---- forward window (a6 / X7 across processes) ----
+int tfsc_fwd_window(tfsc_server* s, void** dev_ptr, size_t* bytes, size_t* slot_bytes) {
+  if (!s || !s->fwd) return fail(TFSC_E_INVALID, "fwd_window: the server has no cluster.endpoints");
+  if (dev_ptr) *dev_ptr = s->fwd->window();
+  if (bytes) *bytes = s->fwd->window_bytes();
+  if (slot_bytes) *slot_bytes = s->fwd->slot_bytes();
+  return s->fwd->rank();
+}
+int tfsc_device_memcpy(void* dst, const void* src, size_t nbytes) {
+  cudaError_t e = cudaMemcpy(dst, src, nbytes, cudaMemcpyDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(TFSC_E_INTERNAL, "device_memcpy: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+int tfsc_fwd_peer_window(tfsc_server* s, int peer_rank, void** dev_ptr, size_t* bytes) {
+  if (!s || !s->fwd || !dev_ptr) return fail(TFSC_E_INVALID, "fwd_peer_window: bad arguments / no cluster.endpoints");
+  return guarded("fwd_peer_window", [&] {
+    std::string err;
+    char* p = s->fwd->peer_window(peer_rank, bytes, &err);
+    if (!p) return fail(TFSC_E_INTERNAL, "%s", err.c_str());
+    *dev_ptr = p;
+    return 0;
+  });
 }
 
 int tfsc_predict_device(tfsc_server* s, int node, const char* model_name, int64_t version, const void* x,
@@ -708,6 +996,22 @@ int tfsc_predict_device(tfsc_server* s, int node, const char* model_name, int64_
   int rc = n->predict_device({model_name, version}, x, rows, y, (cudaStream_t)stream, &err);
   if (rc < 0) return fail(rc, "%s", err.c_str());
   return 0;
+}
+
+int tfsc_node_set_max_resident(tfsc_server* s, int node, int max_concurrent_models) {
+  Node* n = node_at(s, node);
+  if (!n) return TFSC_E_INVALID;
+  if (max_concurrent_models < 1) return fail(TFSC_E_INVALID, "serving.maxConcurrentModels must be >= 1");
+  n->set_max_concurrent_models(max_concurrent_models);
+  return 0;
+}
+
+int tfsc_k_copy_segments(const tfsc_copy_seg* segs, int n, void* stream) {
+  if (int rc = check_device_early()) return rc;
+  if (!segs || n < 0) return fail(TFSC_E_INVALID, "copy_segments: bad arguments");
+  static_assert(sizeof(tfsc_copy_seg) == sizeof(CopySeg), "ABI struct mirrors the kernel's segment");
+  cudaError_t e = launch_copy_segments(reinterpret_cast<const CopySeg*>(segs), n, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "copy_segments: %s", cudaGetErrorString(e));
 }
 
 int tfsc_node_sync(tfsc_server* s, int node) {
@@ -731,6 +1035,15 @@ int tfsc_get_stats(tfsc_server* s, int node, tfsc_stats* out) {
   out->proxy_failures_rest = s->fail_rest;
   out->proxy_failures_grpc = s->fail_grpc;
   out->kernel_launches = kernel_launch_count();
+  if (s->fwd) {
+    const FwdStats& f = s->fwd->stats();
+    out->fwd_out_requests = f.out_requests;
+    out->fwd_in_requests = f.in_requests;
+    out->fwd_out_failures = f.out_failures;
+    out->fwd_peer_bytes_read = f.peer_bytes_read;
+    out->fwd_peer_bytes_written = f.peer_bytes_written;
+    out->fwd_rtt_seconds_sum = (double)f.rtt_ns_sum * 1e-9;
+  }
   return 0;
 }
 

@@ -92,6 +92,68 @@ class Server:
         n = int(np.prod(shape)) if shape else 1
         return y[:n].reshape(shape).copy()
 
+    def _tensors(self, x, out_capacity_elems, input_name):
+        is_int = np.issubdtype(np.asarray(x).dtype, np.integer)
+        x = np.ascontiguousarray(x, dtype=np.int32 if is_int else np.float32)
+        tin = TfscTensor()
+        tin.name = input_name.encode() if input_name else None
+        tin.dtype = _lib.DT_INT32 if is_int else _lib.DT_FLOAT
+        tin.rank = x.ndim
+        for i, d in enumerate(x.shape):
+            tin.shape[i] = d
+        tin.data = x.ctypes.data
+        tin.nbytes = x.nbytes
+        cap = out_capacity_elems if out_capacity_elems is not None else max(x.size, 1) * 4 + 65536
+        y = np.empty(cap, dtype=np.float32)
+        tout = TfscTensor()
+        tout.data = y.ctypes.data
+        tout.nbytes = y.nbytes
+        return x, tin, y, tout
+
+    @staticmethod
+    def _result(y, tout):
+        shape = tuple(tout.shape[i] for i in range(tout.rank))
+        n = int(np.prod(shape)) if shape else 1
+        return y[:n].reshape(shape).copy()
+
+    def predict_deadline(self, model_name: str, version: str, x: np.ndarray, deadline_ns: int, **kw) -> np.ndarray:
+        """tfsc_predict_deadline: deadline is absolute on the clock of now_ns() (0 = none)."""
+        _x, tin, y, tout = self._tensors(x, kw.get("out_capacity_elems"), kw.get("input_name"))
+        check(lib.tfsc_predict_deadline(self._h, model_name.encode(), version.encode(), C.byref(tin), 1, C.byref(tout), 1,
+                                        int(deadline_ns)), "predict")
+        return self._result(y, tout)
+
+    def predict_member(self, member: int, model_name: str, version: str, x: np.ndarray, deadline_ns: int = 0, **kw) -> np.ndarray:
+        """tfsc_predict_member: the cache tier of member `member` (index into gpu.members), no ring lookup."""
+        _x, tin, y, tout = self._tensors(x, kw.get("out_capacity_elems"), kw.get("input_name"))
+        check(lib.tfsc_predict_member(self._h, member, model_name.encode(), version.encode(), C.byref(tin), 1, C.byref(tout), 1,
+                                      int(deadline_ns)), "predict_member")
+        return self._result(y, tout)
+
+    @staticmethod
+    def now_ns() -> int:
+        return lib.tfsc_now_ns()
+
+    def predict_submit(self, model_name: str, version: str, x: np.ndarray, deadline_ns: int = 0, **kw) -> "Ticket":
+        """Asynchronous Predict (tfsc_predict_submit): returns a Ticket; .wait() yields the result."""
+        xk, tin, y, tout = self._tensors(x, kw.get("out_capacity_elems"), kw.get("input_name"))
+        t = C.c_void_p()
+        check(lib.tfsc_predict_submit(self._h, model_name.encode(), version.encode(), C.byref(tin), 1, C.byref(tout), 1,
+                                      int(deadline_ns), C.byref(t)), "predict_submit")
+        return Ticket(t, y, tout)
+
+    def fwd_window(self):
+        """(rank, device pointer, bytes, slot bytes) of this rank's forward window (needs cluster.endpoints)."""
+        p, n, sb = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        rank = check(lib.tfsc_fwd_window(self._h, C.byref(p), C.byref(n), C.byref(sb)), "fwd_window")
+        return rank, p.value, n.value, sb.value
+
+    def fwd_peer_window(self, peer_rank: int):
+        """(device pointer, bytes) of another rank's window mapped into this process (CUDA IPC)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        check(lib.tfsc_fwd_peer_window(self._h, peer_rank, C.byref(p), C.byref(n)), "fwd_peer_window")
+        return p.value, n.value
+
     def grpc_predict(self, request_bytes: bytes) -> bytes:
         resp = C.c_void_p()
         n = C.c_size_t()
@@ -116,6 +178,9 @@ class Server:
         check(lib.tfsc_predict_device(self._h, node, model_name.encode(), version, x_ptr, rows, y_ptr, stream),
               "predict_device")
 
+    def set_max_resident(self, node: int, n: int):
+        check(lib.tfsc_node_set_max_resident(self._h, node, n), "set_max_resident")
+
     def sync(self, node: int = 0):
         check(lib.tfsc_node_sync(self._h, node), "node_sync")
 
@@ -123,3 +188,21 @@ class Server:
         st = TfscStats()
         check(lib.tfsc_get_stats(self._h, node, C.byref(st)), "get_stats")
         return st.as_dict()
+
+
+class Ticket:
+    """An in-flight asynchronous Predict (tfsc_ticket). Keeps the output buffer alive until released."""
+
+    def __init__(self, handle, y, tout):
+        self._t, self._y, self._tout = handle, y, tout
+
+    def wait(self, timeout_s: float | None = None) -> np.ndarray:
+        check(lib.tfsc_predict_wait(self._t, -1 if timeout_s is None else int(timeout_s * 1e9)), "predict_wait")
+        return Server._result(self._y, self._tout)
+
+    def release(self):
+        if self._t:
+            lib.tfsc_predict_release(self._t)
+            self._t = None
+
+    __del__ = release
