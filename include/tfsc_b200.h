@@ -222,6 +222,15 @@ void tfsc_predict_release(tfsc_ticket* ticket);
 /* Same, wire level: serialized tensorflow.serving.PredictRequest in, PredictResponse out
  * (library-owned; tfsc_free). This is what a cgo Predict handler calls. */
 int tfsc_grpc_predict(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len);
+/* proxyServiceServer.Classify / Regress (tfservingproxy.go:173-198) and SessionRun (:233-244), wire level like
+ * tfsc_grpc_predict: serialized ClassificationRequest / RegressionRequest / SessionRunRequest in, the matching response out
+ * (library-owned; tfsc_free). tf.Example inputs are mapped onto the model's input rows through the classify / regress
+ * signatures the bundle declares ("extra_signatures" of the manifest; a SavedModel import carries over the signatures of
+ * saved_model.pb, e.g. half_plus_two's regress_x_to_y / classify_x_to_y on feature "x"). A model without such a signature
+ * answers INVALID_ARGUMENT with TF-Serving's message. MultiInference stays an error (tfservingproxy.go:215-217). */
+int tfsc_grpc_classify(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len);
+int tfsc_grpc_regress(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len);
+int tfsc_grpc_session_run(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len);
 /* RestProxy.Serve (tfservingproxy.go:93-129) with on-GPU execution: GET status / POST :predict.
  * Returns 0 and fills *http_status + body (library-owned; tfsc_free). */
 int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const void* body, size_t body_len,

@@ -13,9 +13,12 @@ DIMS = [256, 520, 136, 32]
 
 
 def _need2():
+    import os
     import torch
+    if os.environ.get("TFSC_REQUIRE_MULTI") == "1":   # a multi-GPU run must not pass by skipping
+        assert torch.cuda.is_available() and torch.cuda.device_count() >= 2, "TFSC_REQUIRE_MULTI=1 needs >= 2 GPUs"
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+        pytest.skip("needs 2 GPUs (the cross-process forward hop is covered on one GPU by tests/test_gpu_forward.py)")
     return torch
 
 

@@ -183,3 +183,69 @@ def test_native_importer_rejects_bad_inputs(tmp_path):
     for cut in range(0, len(gpb), 11):
         open(pb, "wb").write(gpb[:cut])
         assert _native_convert(d, tmp_path / "o6") in (0, _lib.E_INVALID)
+
+
+# ---- f1 pin: fixtures assembled by an independent writer from the reference's own protobuf schema ------------------
+def _write_golden_model(golden, name, version_dir):
+    import base64
+    g = golden("savedmodel_golden.json")["models"][name]
+    for rel, b64 in g["files"].items():
+        p = os.path.join(version_dir, rel)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        with open(p, "wb") as f:
+            f.write(base64.b64decode(b64))
+    return g["expect"]
+
+
+@pytest.mark.parametrize("name", ["half_plus_two", "keras_mlp"])
+def test_golden_savedmodel_written_with_reference_schema_converts(name, golden, tmp_path):
+    """tests/golden/savedmodel_golden.json was produced by python-protobuf from the FileDescriptorProtos embedded in the
+    reference's generated code plus an independent LevelDB-table writer (tests/golden/make_savedmodel_golden.py) -- no code
+    shared with the product. Both importers (native C++ through the C ABI, and the Python twin) must read it."""
+    import base64
+    import ctypes
+    import tfservingcache_b200 as t
+    src = tmp_path / "src" / name / "1"
+    expect = _write_golden_model(golden, name, str(src))
+    outs = {}
+    for impl in ("native", "python"):
+        out = tmp_path / impl / name / "1"
+        if impl == "native":
+            os.makedirs(out)
+            rc = t._lib.lib.tfsc_savedmodel_convert(str(src).encode(), str(out).encode())
+            assert rc >= 0, t._lib.lib.tfsc_last_error()
+            man = json.load(open(out / "tfsc_model.json"))
+        else:
+            man = sm.convert(str(src), str(out))
+        assert man["template"] == expect["template"] and man["signature"] == {"input": expect["input"], "output": expect["output"]}
+        oman, blob = models.load_bundle(str(out))
+        x = np.array(expect["x"], np.float32)
+        y = models.forward(oman, blob, x, np.float64)
+        assert np.max(np.abs(y - np.array(expect["y"]))) <= 1e-5
+        outs[impl] = (open(out / "weights.bin", "rb").read(), json.load(open(out / "tfsc_model.json")))
+    assert outs["native"][0] == outs["python"][0]          # byte-identical bundles from both importers
+    if name == "keras_mlp":
+        got = sm.read_bundle(str(src / "variables" / "variables"))
+        for k, b64 in expect["tensors"].items():
+            assert got[k].astype("<f4").tobytes() == base64.b64decode(b64)
+    # the independent writer's checksum (bitwise CRC-32C) and the product's table-driven one agree on the data shard
+    data = open(src / "variables" / "variables.data-00000-of-00001", "rb").read()
+    assert ctypes.c_uint32(t._lib.lib.tfsc_crc32c(data, len(data))).value == sm.crc32c(data)
+
+
+@pytest.mark.gpu
+def test_golden_half_plus_two_savedmodel_is_served(golden, tmp_path):
+    """BASELINE configs[0]: the half_plus_two SavedModel through diskProvider and REST, on the GPU: [1,2,5] -> [2.5,3,4.5]
+    (deploy/docker-compose/readme.md:40-42), from the independently written fixture."""
+    import torch
+    import tfservingcache_b200 as t
+    assert torch.cuda.is_available()
+    _write_golden_model(golden, "half_plus_two", str(tmp_path / "half_plus_two" / "00000123"))
+    expect = _write_golden_model(golden, "keras_mlp", str(tmp_path / "keras_mlp" / "1"))
+    cfg = {"modelProvider.type": "diskProvider", "modelProvider.diskProvider.baseDir": str(tmp_path), "gpu.devices": [0],
+           "gpu.arenaBytes": 8 << 20, "modelCache.size": 1 << 26, "serving.maxConcurrentModels": 2}
+    with t.Server(cfg) as srv:
+        st, body = srv.rest_handle("POST", "/v1/models/half_plus_two/versions/123:predict", b'{"instances": [1.0, 2.0, 5.0]}')
+        assert st == 200 and json.loads(body) == {"predictions": [2.5, 3.0, 4.5]}
+        y = srv.predict("keras_mlp", "1", np.array(expect["x"], np.float32), input_name="inputs")
+        assert np.max(np.abs(y - np.array(expect["y"]))) <= 1e-4

@@ -106,6 +106,8 @@ _sig("tfsc_fwd_window", C.c_int, vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)
 _sig("tfsc_fwd_peer_window", C.c_int, vp, C.c_int, C.POINTER(vp), C.POINTER(sz))
 _sig("tfsc_device_memcpy", C.c_int, vp, vp, sz)
 _sig("tfsc_grpc_predict", C.c_int, vp, vp, sz, C.POINTER(vp), C.POINTER(sz))
+for _n in ("tfsc_grpc_classify", "tfsc_grpc_regress", "tfsc_grpc_session_run"):
+    _sig(_n, C.c_int, vp, vp, sz, C.POINTER(vp), C.POINTER(sz))
 _sig("tfsc_rest_handle", C.c_int, vp, cp, cp, vp, sz, C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(sz))
 _sig("tfsc_predict_device", C.c_int, vp, C.c_int, cp, i64, vp, i64, vp, vp)
 _sig("tfsc_node_sync", C.c_int, vp, C.c_int)

@@ -81,6 +81,20 @@ bool parse_manifest(const Json& j, ModelDesc* d, std::string* err) {
     d->input_name = sig->get_str("input", "x");
     d->output_name = sig->get_str("output", "y");
   }
+  if (const Json* ex = j.get("extra_signatures")) {
+    for (auto& e : ex->arr) {
+      ExtraSignature g;
+      g.name = e.get_str("name", "");
+      const std::string m = e.get_str("method", "");
+      g.method = m == "classify" ? 1 : m == "regress" ? 2 : 0;
+      g.feature = e.get_str("feature", d->input_name);
+      if (g.name.empty() || g.method == 0) {
+        *err = "extra_signatures entries need a name and method classify|regress";
+        return false;
+      }
+      d->extra_sigs.push_back(g);
+    }
+  }
   d->weights_bytes = (size_t)j.get_int("weights_bytes", 0);
   std::string t = j.get_str("template", "");
   if (t == "affine") {

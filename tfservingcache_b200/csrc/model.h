@@ -38,8 +38,17 @@ struct DenseLayer {
   size_t w_off = 0, b_off = 0;  // bytes into the blob; W row-major [in,out] fp32, b[out]
 };
 
+// classify / regress signatures of a model (tensorflow/serving/{classify,regress}): their input is a list of tf.Example,
+// `feature` names the float feature that holds one input row per example (half_plus_two: "x")
+struct ExtraSignature {
+  std::string name;     // e.g. "regress_x_to_y"
+  int method = 0;       // 1 = classify, 2 = regress
+  std::string feature;
+};
+
 struct ModelDesc {
   Template tmpl = Template::Mlp;
+  std::vector<ExtraSignature> extra_sigs;
   std::vector<DenseLayer> layers;  // Mlp
   size_t a_off = 0, b_off = 0;     // Affine scalars
   size_t weights_bytes = 0;

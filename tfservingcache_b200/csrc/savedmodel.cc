@@ -482,6 +482,22 @@ bool savedmodel_import(const std::string& dir, SavedModelBundle* out, std::strin
   sig_json += ", \"output\": ";
   json_str(out_key, &sig_json);
   sig_json += "}";
+  // classify / regress signatures of the SavedModel are kept (tensorflow/serving/{classify,regress}): their tf.Example
+  // feature is the predict signature's input key (half_plus_two: feature "x" for regress_x_to_y / classify_x_to_y)
+  std::string extra;
+  for (auto& kv : sigs) {
+    const std::string& mth = kv.second.method;
+    const char* kind = mth.size() >= 8 && mth.compare(mth.size() - 8, 8, "classify") == 0 ? "classify"
+                       : mth.size() >= 7 && mth.compare(mth.size() - 7, 7, "regress") == 0 ? "regress" : nullptr;
+    if (!kind) continue;
+    extra += extra.empty() ? "" : ", ";
+    extra += "{\"name\": ";
+    json_str(kv.first, &extra);
+    extra += std::string(", \"method\": \"") + kind + "\", \"feature\": ";
+    json_str(in_key, &extra);
+    extra += "}";
+  }
+  if (!extra.empty()) sig_json += ", \"extra_signatures\": [" + extra + "]";
 
   // ---- affine: y = Add(Mul(a, x), b), scalar variables
   if ((g->op == "Add" || g->op == "AddV2") && g->inputs.size() == 2) {

@@ -529,6 +529,191 @@ static int grpc_predict_impl(tfsc_server* s, const void* req, size_t req_len, vo
   return 0;
 }
 
+static void set_resp_bytes(const std::string& body, void** resp, size_t* resp_len) {
+  char* b = (char*)malloc(body.size() + 1);
+  memcpy(b, body.data(), body.size());
+  b[body.size()] = 0;
+  *resp = b;
+  *resp_len = body.size();
+}
+
+// ---- Classify / Regress (tfservingproxy.go:173-198): tf.Example inputs -> one row per example -> the predict path.
+// method: 1 = classify, 2 = regress. Fills scores [n, per] (classify: per = outputs per example; regress: per == 1).
+static int run_examples(tfsc_server* s, const ExampleRequestView& view, int method, std::vector<float>* scores, int64_t* n_out,
+                        int64_t* per_out, ModelId* id_out, std::string* sig_out, std::string* err, int* code) {
+  const std::string version = std::to_string(view.version);  // clientForSpec: "0" when absent
+  Node* node;
+  ModelId id;
+  int remote = -1;
+  int rc = resolve(s, view.model_name, version, &node, &id, &remote);
+  if (rc < 0) {
+    *err = tfsc_last_error();
+    return rc;
+  }
+  if (!node) {
+    *err = "model " + view.model_name + " is owned by rank " + std::to_string(remote) + "; Classify / Regress are served by the owner";
+    return TFSC_E_NOT_FOUND;
+  }
+  ModelDesc d;
+  rc = node->describe(id, &d, nullptr, err);  // fetchModel first, like every request of the reference
+  if (rc < 0) return rc;
+  const std::string want = view.signature_name.empty() ? "serving_default" : view.signature_name;
+  const ExtraSignature* sg = nullptr;
+  for (auto& e : d.extra_sigs)
+    if (e.name == want) sg = &e;
+  const char* mname = method == 1 ? "tensorflow/serving/classify" : "tensorflow/serving/regress";
+  if (!sg) {
+    // TF-Serving's answers: an unknown signature key, or a signature of the wrong method (classifier.cc / regressor.cc)
+    if (want == "serving_default")
+      *err = std::string("Expected ") + (method == 1 ? "classification" : "regression") + " signature method_name to be " + mname +
+             ". Was: tensorflow/serving/predict";
+    else
+      *err = "Serving signature name: \"" + want + "\" not found in signature def";
+    return TFSC_E_INVALID;
+  }
+  if (sg->method != method) {
+    *err = std::string("Expected ") + (method == 1 ? "classification" : "regression") + " signature method_name to be " + mname +
+           ". Was: " + (sg->method == 1 ? "tensorflow/serving/classify" : "tensorflow/serving/regress");
+    return TFSC_E_INVALID;
+  }
+  if (view.examples.empty()) {
+    *err = "Input is empty";  // TF-Serving: InvalidArgument("Input is empty.")
+    return TFSC_E_INVALID;
+  }
+  const int64_t per_row = d.tmpl == Template::Affine ? 1 : d.in_dim;
+  if (d.input_dtype != TFSC_DT_FLOAT) {
+    *err = "the model's input is not a float tensor: no tf.Example signature";
+    return TFSC_E_INVALID;
+  }
+  std::vector<float> x;
+  x.reserve((size_t)view.examples.size() * per_row);
+  for (size_t i = 0; i < view.examples.size(); ++i) {
+    const std::vector<float>* f = view.examples[i].find(sg->feature);
+    if (!f || (int64_t)f->size() != per_row) {
+      *err = "example " + std::to_string(i) + ": feature '" + sg->feature + "' must hold " + std::to_string(per_row) +
+             " float value(s), found " + (f ? std::to_string(f->size()) : std::string("none"));
+      return TFSC_E_INVALID;
+    }
+    x.insert(x.end(), f->begin(), f->end());
+  }
+  const int64_t n = (int64_t)view.examples.size();
+  const int64_t per = d.tmpl == Template::Affine ? 1 : d.out_dim;
+  if (method == 2 && per != 1) {
+    *err = "Expected output Tensor shape to be either [batch_size] or [batch_size, 1] but got [" + std::to_string(n) + "," +
+           std::to_string(per) + "]";  // regressor.cc
+    return TFSC_E_INVALID;
+  }
+  scores->assign((size_t)(n * per), 0.f);
+  auto alloc = [&](const ModelDesc&, int64_t rows) -> void* { return rows == n ? scores->data() : nullptr; };
+  rc = node->predict_host(id, x.data(), (int64_t)x.size(), TFSC_DT_FLOAT, alloc, nullptr, nullptr, err);
+  if (rc < 0) return rc;
+  *n_out = n;
+  *per_out = per;
+  *id_out = id;
+  *sig_out = want;
+  (void)code;
+  return 0;
+}
+
+static int grpc_examples_impl(tfsc_server* s, int method, const void* req, size_t req_len, void** resp, size_t* resp_len) {
+  if (!s || !req || !resp || !resp_len) return fail(TFSC_E_INVALID, "grpc_classify/regress: bad arguments");
+  s->req_grpc++;  // promRequestsTotal{grpc}, tfservingproxy.go:174,188
+  ExampleRequestView view;
+  std::string err;
+  if (!decode_example_request(req, req_len, &view, &err)) {
+    s->fail_grpc++;
+    return fail(TFSC_E_INVALID, "%s", err.c_str());
+  }
+  std::vector<float> scores;
+  int64_t n = 0, per = 0;
+  ModelId id;
+  std::string sig;
+  int rc = run_examples(s, view, method, &scores, &n, &per, &id, &sig, &err, nullptr);
+  if (rc < 0) {
+    s->fail_grpc++;
+    return fail(rc, "%s", err.c_str());
+  }
+  const std::string out = method == 1 ? encode_classification_response(view.model_name, id.version, sig, scores.data(), n, per)
+                                      : encode_regression_response(view.model_name, id.version, sig, scores.data(), n);
+  set_resp_bytes(out, resp, resp_len);
+  return 0;
+}
+
+static int grpc_session_run_impl(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len) {
+  if (!s || !req || !resp || !resp_len) return fail(TFSC_E_INVALID, "grpc_session_run: bad arguments");
+  s->req_grpc++;  // tfservingproxy.go:234
+  SessionRunView view;
+  std::string err;
+  if (!decode_session_run_request(req, req_len, &view, &err)) {
+    s->fail_grpc++;
+    return fail(TFSC_E_INVALID, "%s", err.c_str());
+  }
+  Node* node;
+  ModelId id;
+  int remote = -1;
+  int rc = resolve(s, view.model_name, std::to_string(view.version), &node, &id, &remote);
+  if (rc < 0) {
+    s->fail_grpc++;
+    return rc;
+  }
+  auto strip = [](const std::string& t) { return t.size() > 2 && t.compare(t.size() - 2, 2, ":0") == 0 ? t.substr(0, t.size() - 2) : t; };
+  if (view.feeds.size() != 1 || view.fetch.size() != 1 || !view.target.empty()) {
+    if (node) node->fetch(id, nullptr, &err);
+    s->fail_grpc++;
+    return fail(TFSC_E_INVALID, "SessionRun on a model template takes exactly one feed (the signature input) and one fetch (its output)");
+  }
+  const TensorView& tv = view.feeds[0];
+  const void* xdata = nullptr;
+  int64_t n = 0;
+  std::vector<float> scratch;
+  std::vector<int32_t> iscratch;
+  bool ok;
+  if (tv.dtype == TFSC_DT_INT32) {
+    const int32_t* ip = nullptr;
+    ok = tensor_i32(tv, &ip, &n, &iscratch, &err);
+    xdata = ip;
+  } else {
+    const float* fp = nullptr;
+    ok = tensor_f32(tv, &fp, &n, &scratch, &err);
+    xdata = fp;
+  }
+  if (!ok) {
+    s->fail_grpc++;
+    return fail(TFSC_E_INVALID, "%s", err.c_str());
+  }
+  char* buf = nullptr;
+  size_t total = 0;
+  std::string bad;
+  auto alloc = [&](const ModelDesc& d, int64_t rows) -> void* {
+    if (strip(tv.name) != d.input_name || strip(view.fetch[0]) != d.output_name) {
+      bad = "feed / fetch do not name the model's tensors (feed '" + d.input_name + ":0', fetch '" + d.output_name + ":0')";
+      return nullptr;
+    }
+    std::vector<int64_t> sh;
+    if (!out_shape(d, rows, tv.shape, &sh, &bad)) return nullptr;
+    std::string prefix, suffix;
+    session_run_response_frame(view.model_name, id.version, view.signature_name, view.fetch[0], sh, &prefix, &suffix);
+    int64_t on = 1;
+    for (auto v : sh) on *= v;
+    total = prefix.size() + (size_t)on * 4 + suffix.size();
+    buf = (char*)malloc(total ? total : 1);
+    if (!buf) return nullptr;
+    memcpy(buf, prefix.data(), prefix.size());
+    memcpy(buf + prefix.size() + (size_t)on * 4, suffix.data(), suffix.size());
+    return buf + prefix.size();
+  };
+  rc = run_predict(s, node, remote, id, xdata, n, tv.dtype == TFSC_DT_INT32 ? TFSC_DT_INT32 : TFSC_DT_FLOAT, alloc, &err);
+  if (rc < 0) {
+    free(buf);
+    s->fail_grpc++;
+    if (!bad.empty()) return fail(TFSC_E_INVALID, "%s", bad.c_str());
+    return fail(rc, "%s", err.c_str());
+  }
+  *resp = buf;
+  *resp_len = total;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ REST ------
 static const char* state_name(int st) {
   switch (st) {
@@ -759,9 +944,70 @@ static int rest_handle_impl(tfsc_server* s, const char* method, const char* url,
     return 0;
   }
   if (m == "POST" && (tail == ":classify" || tail == ":regress")) {
-    rc = node->fetch(id, nullptr, &err);
-    if (rc < 0) return fail_http(http_for(rc), err);
-    return fail_http(400, "Expected classification/regression signature; model " + name + " exports a predict signature only");
+    // TF-Serving REST: {"signature_name": ..., "context": {feature: value}, "examples": [{feature: value | [values]}, ...]}
+    const int method = tail == ":classify" ? 1 : 2;
+    Json req;
+    bool parsed = json_parse(std::string((const char*)body, body_len), &req, &err) && req.type == Json::Obj;
+    const Json* examples = parsed ? req.get("examples") : nullptr;
+    if (!parsed || !examples || examples->type != Json::Arr) {
+      std::string e2;
+      rc = node->fetch(id, nullptr, &e2);
+      if (rc < 0) return fail_http(http_for(rc), e2);
+      return fail_http(400, parsed ? "JSON body must contain an 'examples' list" : err);
+    }
+    ExampleRequestView view;
+    view.model_name = name;
+    view.version = id.version;
+    view.has_version = true;
+    view.signature_name = req.get_str("signature_name", "");
+    auto add_features = [&](const Json& obj, ExampleView* ex) {
+      if (obj.type != Json::Obj) return false;
+      for (auto& kv : obj.obj) {
+        std::vector<float> vals;
+        if (kv.second.type == Json::Num) vals.push_back((float)kv.second.num);
+        else if (kv.second.type == Json::Arr) {
+          for (auto& e : kv.second.arr)
+            if (e.type == Json::Num) vals.push_back((float)e.num);
+            else return false;
+        } else continue;  // string features are not numeric inputs
+        if (!ex->find(kv.first)) ex->features.emplace_back(kv.first, vals);
+      }
+      return true;
+    };
+    bool ok = true;
+    for (auto& e : examples->arr) {
+      ExampleView ex;
+      ok = ok && add_features(e, &ex);
+      if (const Json* ctx = req.get("context")) ok = ok && add_features(*ctx, &ex);
+      view.examples.push_back(std::move(ex));
+    }
+    if (!ok) return fail_http(400, "examples must be objects mapping feature names to numbers or lists of numbers");
+    std::vector<float> scores;
+    int64_t n = 0, per = 0;
+    ModelId rid;
+    std::string sig;
+    rc = run_examples(s, view, method, &scores, &n, &per, &rid, &sig, &err, nullptr);
+    if (rc < 0) return fail_http(rc == TFSC_E_INVALID ? 400 : http_for(rc), err);
+    std::string b = "{\n    \"results\": [";
+    for (int64_t i = 0; i < n; ++i) {
+      if (i) b += ", ";
+      if (method == 2) {
+        json_float(scores[(size_t)i], &b);
+      } else {
+        b += "[";
+        for (int64_t k = 0; k < per; ++k) {
+          if (k) b += ", ";
+          b += "[\"\", ";
+          json_float(scores[(size_t)(i * per + k)], &b);
+          b += "]";
+        }
+        b += "]";
+      }
+    }
+    b += "]\n}";
+    *http_status = 200;
+    set_resp(b, resp, resp_len);
+    return 0;
   }
   return fail_http(400, "Malformed request: " + m + " " + u);
 }
@@ -789,6 +1035,15 @@ int tfsc_predict_member(tfsc_server* s, int member, const char* model_name, cons
 int64_t tfsc_now_ns(void) { return Node::now_ns(); }
 int tfsc_grpc_predict(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len) {
   return guarded("grpc_predict", [&] { return grpc_predict_impl(s, req, req_len, resp, resp_len); });
+}
+int tfsc_grpc_classify(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len) {
+  return guarded("grpc_classify", [&] { return grpc_examples_impl(s, 1, req, req_len, resp, resp_len); });
+}
+int tfsc_grpc_regress(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len) {
+  return guarded("grpc_regress", [&] { return grpc_examples_impl(s, 2, req, req_len, resp, resp_len); });
+}
+int tfsc_grpc_session_run(tfsc_server* s, const void* req, size_t req_len, void** resp, size_t* resp_len) {
+  return guarded("grpc_session_run", [&] { return grpc_session_run_impl(s, req, req_len, resp, resp_len); });
 }
 int tfsc_rest_handle(tfsc_server* s, const char* method, const char* url, const void* body, size_t body_len,
                      int* http_status, void** resp, size_t* resp_len) {

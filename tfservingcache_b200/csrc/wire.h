@@ -57,4 +57,45 @@ void predict_response_frame(const std::string& model_name, int64_t version, cons
                             const std::string& output_name, const std::vector<int64_t>& shape, std::string* prefix,
                             std::string* suffix);
 
+// ---- Classify / Regress (tfservingproxy.go:173-198): ClassificationRequest / RegressionRequest{model_spec=1, input=2
+// Input{example_list=1{examples=1}, example_list_with_context=2{examples=1, context=2}}}, tf.Example{features=1{feature=1
+// map<string, Feature{bytes_list=1, float_list=2{value=1 packed}, int64_list=3}>}} (proto/tensorflow/serving/
+// {classification,regression,input}.pb.go, proto/tensorflow/core/example/{example,feature}.pb.go)
+struct ExampleView {
+  std::vector<std::pair<std::string, std::vector<float>>> features;  // numeric features (int64 values converted)
+  const std::vector<float>* find(const std::string& key) const {
+    for (auto& f : features)
+      if (f.first == key) return &f.second;
+    return nullptr;
+  }
+};
+struct ExampleRequestView {
+  std::string model_name, signature_name;
+  bool has_version = false;
+  int64_t version = 0;
+  std::vector<ExampleView> examples;  // context features (example_list_with_context) are merged into every example
+};
+bool decode_example_request(const void* data, size_t len, ExampleRequestView* out, std::string* err);
+// ClassificationResponse{result=1{classifications=1[{classes=1[{label=1, score=2}]}]}, model_spec=2}: n examples x c scores
+std::string encode_classification_response(const std::string& model_name, int64_t version, const std::string& signature,
+                                           const float* scores, int64_t n, int64_t c);
+// RegressionResponse{result=1{regressions=1[{value=1}]}, model_spec=2}
+std::string encode_regression_response(const std::string& model_name, int64_t version, const std::string& signature,
+                                       const float* values, int64_t n);
+
+// ---- SessionRun (tfservingproxy.go:233-244): SessionRunRequest{model_spec=1, feed=2[NamedTensorProto{name=1, tensor=2}],
+// fetch=3, target=4}; SessionRunResponse{tensor=1[NamedTensorProto], model_spec=3} (session_service.pb.go, named_tensor.pb.go)
+struct SessionRunView {
+  std::string model_name, signature_name;
+  bool has_version = false;
+  int64_t version = 0;
+  std::vector<TensorView> feeds;        // TensorView.name = the fed tensor name ("x:0")
+  std::vector<std::string> fetch, target;
+};
+bool decode_session_run_request(const void* data, size_t len, SessionRunView* out, std::string* err);
+// response split around the float payload like predict_response_frame
+void session_run_response_frame(const std::string& model_name, int64_t version, const std::string& signature_name,
+                                const std::string& tensor_name, const std::vector<int64_t>& shape, std::string* prefix,
+                                std::string* suffix);
+
 }  // namespace tfsc

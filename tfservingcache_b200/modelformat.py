@@ -14,7 +14,7 @@ def _align256(x: int) -> int:
     return (x + 255) & ~255
 
 
-def write_mlp_bundle(version_dir: str, weights, biases, activations=None, input_name="x", output_name="y"):
+def write_mlp_bundle(version_dir: str, weights, biases, activations=None, input_name="x", output_name="y", extra_signatures=None):
     n = len(weights)
     if activations is None:
         activations = ["relu"] * (n - 1) + ["linear"]
@@ -32,16 +32,20 @@ def write_mlp_bundle(version_dir: str, weights, biases, activations=None, input_
         blob[L["b_offset"] // 4: L["b_offset"] // 4 + b.size] = np.asarray(b, np.float32).ravel()
     man = {"format": "tfsc-b200-v1", "template": "mlp", "dtype": "float32",
            "signature": {"input": input_name, "output": output_name}, "layers": layers, "weights_bytes": off}
+    if extra_signatures:   # classify / regress signatures: [{"name", "method": "classify"|"regress", "feature"}]
+        man["extra_signatures"] = list(extra_signatures)
     _write(version_dir, man, blob)
     return man
 
 
-def write_affine_bundle(version_dir: str, a: float, b: float, input_name="x", output_name="y"):
+def write_affine_bundle(version_dir: str, a: float, b: float, input_name="x", output_name="y", extra_signatures=None):
     blob = np.zeros(128, dtype=np.float32)
     blob[0], blob[64] = a, b
     man = {"format": "tfsc-b200-v1", "template": "affine", "dtype": "float32",
            "signature": {"input": input_name, "output": output_name}, "a_offset": 0, "b_offset": 256,
            "weights_bytes": 512}
+    if extra_signatures:
+        man["extra_signatures"] = list(extra_signatures)
     _write(version_dir, man, blob)
     return man
 

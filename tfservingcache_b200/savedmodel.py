@@ -255,6 +255,9 @@ def convert(saved_model_dir: str, out_version_dir: str, signature: str = "servin
         raise ValueError("only single-input single-output predict signatures are supported")
     (in_key, in_t), (out_key, out_t) = next(iter(ins.items())), next(iter(outs.items()))
     x = _node(in_t)
+    # classify / regress signatures are kept; their tf.Example feature is the predict input key (half_plus_two: "x")
+    extra = [{"name": k, "method": "classify" if m.endswith("classify") else "regress", "feature": in_key}
+             for k, (_i, _o, m) in sorted(sigs.items()) if m.endswith("classify") or m.endswith("regress")]
 
     def is_x(t):
         n = _node(t)
@@ -276,7 +279,7 @@ def convert(saved_model_dir: str, out_version_dir: str, signature: str = "servin
                     a_var, b_var = _resolve_variable(nodes, _node(a_t), variables), _resolve_variable(nodes, _node(b_t), variables)
                     if a_var and b_var and is_x(x_t) and variables[a_var].size == 1 and variables[b_var].size == 1:
                         return modelformat.write_affine_bundle(out_version_dir, float(variables[a_var].ravel()[0]),
-                                                               float(variables[b_var].ravel()[0]), in_key, out_key)
+                                                               float(variables[b_var].ravel()[0]), in_key, out_key, extra)
     # ---- MLP: walk back from the output through [Relu] <- BiasAdd/Add <- MatMul
     layers = []
     while not is_x(cur):
@@ -305,7 +308,7 @@ def convert(saved_model_dir: str, out_version_dir: str, signature: str = "servin
         raise ValueError("graph is neither y = a*x + b nor a dense MLP")
     layers.reverse()
     return modelformat.write_mlp_bundle(out_version_dir, [l[0] for l in layers], [l[1] for l in layers], [l[2] for l in layers],
-                                        in_key, out_key)
+                                        in_key, out_key, extra)
 
 
 def import_tree(base_dir: str, force: bool = False) -> list:

@@ -101,8 +101,7 @@ def make_grpc_server(srv: Server, port: int, max_msg: int = 16 * 1024 * 1024, wo
 
     def unsupported(name):
         def fn(request: bytes, context):
-            # MultiInference is rejected by the reference too (tfservingproxy.go:215-217); Classify/Regress need
-            # tf.Example signatures that the predict-only model templates of this build do not export
+            # MultiInference is rejected by the reference too (tfservingproxy.go:215-217)
             context.abort(grpc.StatusCode.UNIMPLEMENTED, f"{name} not supported")
         return fn
 
@@ -179,16 +178,26 @@ def make_grpc_server(srv: Server, port: int, max_msg: int = 16 * 1024 * 1024, wo
     def health_check(request: bytes, context):
         return b"\x08\x01" if health_status["serving"] else b"\x08\x02"  # HealthCheckResponse{status}
 
+    def wire_call(fn_name):
+        # Classify / Regress / SessionRun (tfservingproxy.go:173-198,233-244): serialized request in, response out
+        def fn(request: bytes, context):
+            try:
+                return getattr(srv, fn_name)(request)
+            except _lib.TfscError as e:
+                context.abort(getattr(grpc.StatusCode, _GRPC_CODE.get(e.code, "INTERNAL")), str(e))
+        return fn
+
     methods = {"Predict": grpc.unary_unary_rpc_method_handler(predict, ident, ident),
-               "GetModelMetadata": grpc.unary_unary_rpc_method_handler(get_model_metadata, ident, ident)}
-    for m in ("Classify", "Regress", "MultiInference"):
-        methods[m] = grpc.unary_unary_rpc_method_handler(unsupported(m), ident, ident)
+               "GetModelMetadata": grpc.unary_unary_rpc_method_handler(get_model_metadata, ident, ident),
+               "Classify": grpc.unary_unary_rpc_method_handler(wire_call("grpc_classify"), ident, ident),
+               "Regress": grpc.unary_unary_rpc_method_handler(wire_call("grpc_regress"), ident, ident),
+               "MultiInference": grpc.unary_unary_rpc_method_handler(unsupported("MultiInference"), ident, ident)}
     server = grpc.server(futures.ThreadPoolExecutor(max_workers=workers),
                          options=[("grpc.max_receive_message_length", max_msg), ("grpc.max_send_message_length", max_msg)])
     server.add_generic_rpc_handlers((
         grpc.method_handlers_generic_handler("tensorflow.serving.PredictionService", methods),
         grpc.method_handlers_generic_handler("tensorflow.serving.SessionService",
-                                             {"SessionRun": grpc.unary_unary_rpc_method_handler(unsupported("SessionRun"), ident, ident)}),
+                                             {"SessionRun": grpc.unary_unary_rpc_method_handler(wire_call("grpc_session_run"), ident, ident)}),
         grpc.method_handlers_generic_handler("tensorflow.serving.ModelService", {
             "GetModelStatus": grpc.unary_unary_rpc_method_handler(get_model_status, ident, ident),
             "HandleReloadConfigRequest": grpc.unary_unary_rpc_method_handler(handle_reload_config, ident, ident)}),

@@ -163,6 +163,24 @@ class Server:
         finally:
             lib.tfsc_free(resp)
 
+    def _wire_call(self, fn, request_bytes: bytes, where: str) -> bytes:
+        resp = C.c_void_p()
+        n = C.c_size_t()
+        check(fn(self._h, request_bytes, len(request_bytes), C.byref(resp), C.byref(n)), where)
+        try:
+            return C.string_at(resp, n.value)
+        finally:
+            lib.tfsc_free(resp)
+
+    def grpc_classify(self, request_bytes: bytes) -> bytes:
+        return self._wire_call(lib.tfsc_grpc_classify, request_bytes, "grpc_classify")
+
+    def grpc_regress(self, request_bytes: bytes) -> bytes:
+        return self._wire_call(lib.tfsc_grpc_regress, request_bytes, "grpc_regress")
+
+    def grpc_session_run(self, request_bytes: bytes) -> bytes:
+        return self._wire_call(lib.tfsc_grpc_session_run, request_bytes, "grpc_session_run")
+
     def rest_handle(self, method: str, url: str, body: bytes = b""):
         st = C.c_int()
         resp = C.c_void_p()
