@@ -315,6 +315,26 @@ class NvmlSampler:
 
 
 # ------------------------------------------------------------------------------- b200 impl ------
+def pin_to_gpu_numa(gpu_index):
+    """Bind this rank (and every thread it will start: client threads, batcher, completer, forwarder) to the CPUs NVML lists as
+    local to its GPU (topo: GPUs 0-3 <-> CPUs 0-31,64-95, GPUs 4-7 <-> 32-63,96-127 on the 8-GPU box). Pinned staging memory is
+    then allocated on the GPU's NUMA node and the PCIe path of the zero-copy gather / scatter does not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} CPUs local to GPU {gpu_index}"
+    except Exception as ex:  # never fatal
+        return f"not pinned ({type(ex).__name__})"
+    return "not pinned"
+
+
 def workload_string(models_per_gpu, dims, replicas, pick_policy):
     """config.workload, identical for the b200 arm and the reference arm (same workload, two implementations)"""
     model_bytes = sum(dims[i] * dims[i + 1] * 4 + dims[i + 1] * 4 for i in range(len(dims) - 1))
@@ -382,6 +402,7 @@ def run_b200(args):
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     assert torch.cuda.is_available(), "bench.py needs a B200; the library has no CPU fallback"
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dims = args.dims or DIMS
@@ -696,7 +717,7 @@ def run_b200(args):
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
     achieved = alg_bytes / (elapsed_ms * 1e-3) / 1e9  # this rank's dense launches are the whole timed region
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "dense_stream_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "dense_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
 
@@ -732,7 +753,7 @@ def run_b200(args):
                        "models_total": wl["n_models"], "tick_requests_per_gpu": args.tick, "max_rows_per_pass": "8 (SIMT) / 64 (tcgen05 3xTF32)",
                        "l2": "inputs larger than L2 (>=1 GB of weights streamed per model pass); L2 flushed before timing",
                        "arena_gib": round(arena / 2**30, 1), "host_tier_gib": round(host_gib, 1), "cold_load_s": round(load_s, 1),
-                       "preheat_s": args.preheat_s, "samplers": args.samplers},
+                       "preheat_s": args.preheat_s, "samplers": args.samplers, "cpu_affinity": numa},
             "e2e": {"value": round(e2e_val, 1), "unit": "req/s",
                     "h2d_bytes_per_step": int((ste1["h2d_input_bytes"] - ste0["h2d_input_bytes"] + ste1["h2d_weight_bytes"] - ste0["h2d_weight_bytes"]) / e2e_steps),
                     "d2h_bytes_per_step": int((ste1["d2h_output_bytes"] - ste0["d2h_output_bytes"]) / e2e_steps),

@@ -167,6 +167,8 @@ typedef struct tfsc_stats {
   /* forward hop (a6): requests sent to / received from other ranks, bytes the owner moved over NVLink */
   int64_t fwd_out_requests, fwd_in_requests, fwd_out_failures, fwd_peer_bytes_read, fwd_peer_bytes_written;
   double fwd_rtt_seconds_sum;
+  /* HBM arena defragmentation: passes that moved resident blocks (device-to-device) and the bytes they moved */
+  int64_t arena_compactions, arena_compacted_bytes;
 } tfsc_stats;
 
 tfsc_server* tfsc_server_create(const char* config_json); /* main.go:45-113 */

@@ -38,7 +38,8 @@ class TfscStats(C.Structure):
         "arena_bytes_used", "arena_bytes_capacity", "resident_models", "host_models")] + [
         ("cache_duration_seconds_sum", C.c_double), ("cache_fetch_duration_seconds_sum", C.c_double)] + [
         (n, C.c_int64) for n in ("fwd_out_requests", "fwd_in_requests", "fwd_out_failures", "fwd_peer_bytes_read",
-                                 "fwd_peer_bytes_written")] + [("fwd_rtt_seconds_sum", C.c_double)]
+                                 "fwd_peer_bytes_written")] + [("fwd_rtt_seconds_sum", C.c_double)] + [
+        ("arena_compactions", C.c_int64), ("arena_compacted_bytes", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

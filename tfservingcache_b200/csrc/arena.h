@@ -63,6 +63,23 @@ class Arena {
     return m;
   }
   size_t blocks() const { return live_.size(); }
+  size_t aligned(size_t bytes) const {
+    size_t need = (bytes + align_ - 1) / align_ * align_;
+    return need ? need : align_;
+  }
+  // after a compaction: the complete list of live blocks (offset, aligned length), address-ordered and non-overlapping
+  void relayout(const std::map<size_t, size_t>& live) {
+    live_ = live;
+    free_.clear();
+    used_ = 0;
+    size_t cur = 0;
+    for (auto& kv : live_) {
+      if (kv.first > cur) free_[cur] = kv.first - cur;
+      cur = kv.first + kv.second;
+      used_ += kv.second;
+    }
+    if (cur < cap_) free_[cur] = cap_ - cur;
+  }
 
  private:
   size_t cap_ = 0, align_ = 1024, used_ = 0;

@@ -254,6 +254,51 @@ void Node::unpin(const std::shared_ptr<DeviceModel>& dm) {
   }
 }
 
+bool Node::compact_locked() {
+  std::map<size_t, std::shared_ptr<DeviceModel>> by_off;
+  for (auto& kv : dev_)
+    if (kv.second->dptr) by_off[kv.second->off] = kv.second;
+  std::map<size_t, size_t> layout;
+  size_t cursor = 0;
+  bool moved = false;
+  for (auto& kv : by_off) {
+    const std::shared_ptr<DeviceModel>& d = kv.second;
+    const size_t len = arena_.aligned(d->bytes);
+    refresh_state_locked(d.get());
+    const bool idle = d->state == TFSC_STATE_AVAILABLE && d->inflight == 0 && d->ready_seen && d->ready;
+    const size_t delta = d->off > cursor ? d->off - cursor : 0;
+    // a block slides down by `delta`; source and destination overlap when delta < len, so the copy goes forward in chunks of
+    // at most delta bytes (each chunk's destination lies below everything not copied yet). Tiny deltas are not worth it.
+    if (idle && delta > 0 && delta >= len / 64) {
+      cudaError_t e = cudaSuccess;
+      for (size_t done = 0; done < d->bytes && e == cudaSuccess; done += delta) {
+        const size_t n = d->bytes - done < delta ? d->bytes - done : delta;
+        e = cudaMemcpyAsync(slab_ + cursor + done, slab_ + d->off + done, n, cudaMemcpyDeviceToDevice, copy_);
+      }
+      if (e == cudaSuccess) e = cudaEventRecord(d->ready, copy_);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        layout[d->off] = len;  // keep it where it is (a partially issued copy only wrote below the block's own start)
+        cursor = d->off + len;
+        continue;
+      }
+      d->off = cursor;
+      d->dptr = slab_ + cursor;
+      d->state = TFSC_STATE_LOADING;  // launches wait for the copy-stream event, exactly as after a page-in
+      d->ready_seen = false;
+      compacted_bytes_ += (int64_t)d->bytes;
+      moved = true;
+    }
+    layout[d->off] = len;
+    cursor = d->off + len;
+  }
+  if (moved) {
+    arena_.relayout(layout);
+    ++compactions_;
+  }
+  return moved;
+}
+
 int Node::reload_locked(std::unique_lock<std::mutex>& lk, const ModelId& want, std::string* err) {
   const auto deadline = Clock::now() + std::chrono::duration<double>(cfg_.fetch_timeout_s);
   for (;;) {
@@ -294,8 +339,14 @@ int Node::reload_locked(std::unique_lock<std::mutex>& lk, const ModelId& want, s
       if (hit == host_.end()) continue;
       size_t off;
       if (!arena_.alloc(hit->second->bytes, &off)) {
-        if (m.id == want) break;  // must wait for space
-        continue;                 // other prefix members are paged in opportunistically
+        // enough free bytes in total but no hole large enough (mixed 102 MB / 438 MB / 1 GB models): pack the idle
+        // resident blocks together with device-to-device copies (~3 TB/s) instead of evicting down the LRU and paying
+        // PCIe reloads (~55 GB/s) later
+        const bool fragmented = arena_.capacity() - arena_.used() >= arena_.aligned(hit->second->bytes);
+        if (!(m.id == want && fragmented && compact_locked() && arena_.alloc(hit->second->bytes, &off))) {
+          if (m.id == want) break;  // must wait for space
+          continue;                 // other prefix members are paged in opportunistically
+        }
       }
       auto nd = std::make_shared<DeviceModel>();
       nd->id = m.id;
@@ -503,6 +554,8 @@ void Node::stats(tfsc_stats* s) {
   s->evictions_host += ev_host_;
   s->evictions_hbm += ev_hbm_;
   s->h2d_weight_bytes += h2d_weights_;
+  s->arena_compactions += compactions_;
+  s->arena_compacted_bytes += compacted_bytes_;
   s->h2d_input_bytes += h2d_inputs_.load();
   s->d2h_output_bytes += d2h_outputs_.load();
   s->batches += batches_.load();

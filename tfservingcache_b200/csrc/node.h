@@ -142,6 +142,7 @@ class Node {
   void begin_unload_locked(const std::shared_ptr<DeviceModel>& d);
   void release_locked(const std::shared_ptr<DeviceModel>& d);
   void reap_locked();
+  bool compact_locked();  // slide idle resident blocks together (D2D) when the arena is fragmented; true if anything moved
   void on_host_evict_locked(const CachedModel& m);
   void refresh_state_locked(DeviceModel* d);
   void* host_alloc(size_t bytes, std::function<void(void*, size_t)>* release);
@@ -198,7 +199,7 @@ class Node {
   bool stop_ = false, batcher_done_ = false;
 
   // stats (guarded by mu_ unless atomic)
-  int64_t total_ = 0, hits_ = 0, misses_ = 0, ev_host_ = 0, ev_hbm_ = 0, h2d_weights_ = 0;
+  int64_t total_ = 0, hits_ = 0, misses_ = 0, ev_host_ = 0, ev_hbm_ = 0, h2d_weights_ = 0, compactions_ = 0, compacted_bytes_ = 0;
   std::atomic<int64_t> h2d_inputs_{0}, d2h_outputs_{0}, batches_{0}, batched_rows_{0};
   double cache_dur_ = 0, fetch_dur_ = 0;
 };
