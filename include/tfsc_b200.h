@@ -302,6 +302,11 @@ int tfsc_k_gemm(const float* a, const float* b, const float* bias, const float* 
 /* the same GEMM on tcgen05 / TMEM (3xTF32, fp32-accurate): m >= 64, n >= 64, n % 32 == 0, k >= 32, lda % 4 == 0 */
 int tfsc_k_gemm_tc(const float* a, const float* b, const float* bias, const float* r, float* c, int m, int n, int k, int lda,
                    int act, void* stream);
+/* X4: implicit-GEMM convolution on tcgen05 / TMEM (3xTF32): y[B,OH,OW,cout] = act(conv2d(x[B,H,W,C] NHWC, w[KH,KW,C,cout] HWIO)
+ * + bias (+ r)); the patch tiles are gathered from x by TMA im2col tensor maps, no patch matrix is materialised.
+ * c % 32 == 0, cout >= 64 and % 32 == 0, batch*OH*OW >= 64. act: 0 none, 1 relu, 2 gelu, 3 tanh. */
+int tfsc_k_conv_tc(const float* x, const float* w, const float* bias, const float* r, float* y, int batch, int h, int wd, int c,
+                   int kh, int kw, int stride, int pad, int cout, int act, void* stream);
 /* col[(b*OH+oh)*OW+ow][(kh*KW+kw)*C+c] patch matrix with row stride ldc >= KH*KW*C (zero padded) */
 int tfsc_k_im2col(const float* x, float* col, int batch, int h, int w, int c, int kh, int kw, int stride, int pad, int ldc,
                   void* stream);

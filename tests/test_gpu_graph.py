@@ -99,6 +99,35 @@ def test_conv_as_im2col_gemm_matches_torch(h, c, kh, stride, pad, cout):
     assert _err(y.cpu().numpy().reshape(bsz, oh, oh, cout), ref) <= TOL
 
 
+@pytest.mark.parametrize("h,c,kh,stride,pad,cout,bsz", [(14, 64, 3, 1, 1, 64, 3), (14, 32, 3, 2, 1, 96, 5), (9, 64, 1, 2, 0, 128, 4),
+                                                         (28, 128, 3, 1, 1, 128, 2), (7, 512, 3, 1, 1, 512, 8), (56, 64, 3, 1, 1, 64, 1),
+                                                         (12, 96, 5, 1, 2, 160, 2), (15, 64, 3, 2, 1, 64, 3)])
+@pytest.mark.parametrize("act,with_res", [(1, True), (0, False)])
+def test_implicit_gemm_conv_matches_torch(h, c, kh, stride, pad, cout, bsz, act, with_res):
+    """X4: conv as implicit GEMM -- the A tiles come from TMA im2col tensor maps over the NHWC activations (padding = TMA
+    zero fill, stride = traversal stride), tcgen05 3xTF32, bias / residual / ReLU in the epilogue. vs torch conv2d fp64."""
+    torch = _torch()
+    rng = np.random.default_rng(h * 31 + c + kh + stride)
+    x = rng.standard_normal((bsz, h, h, c)).astype(np.float32)
+    w = (rng.standard_normal((kh, kh, c, cout)) / np.sqrt(kh * kh * c)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    oh = (h + 2 * pad - kh) // stride + 1
+    r = rng.standard_normal((bsz, oh, oh, cout)).astype(np.float32)
+    xd, wd, bd, rd = (torch.from_numpy(v).cuda() for v in (x, w, b, r))
+    y = torch.full((bsz, oh, oh, cout), float("nan"), device="cuda")
+    t._lib.check(lib.tfsc_k_conv_tc(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), rd.data_ptr() if with_res else None, y.data_ptr(),
+                                    bsz, h, h, c, kh, kh, stride, pad, cout, act, None), "conv_tc")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x).double().permute(0, 3, 1, 2), torch.from_numpy(w).double().permute(3, 2, 0, 1),
+                                     torch.from_numpy(b).double(), stride=stride, padding=pad).permute(0, 2, 3, 1)
+    if with_res:
+        ref = ref + torch.from_numpy(r).double()
+    if act == 1:
+        ref = torch.relu(ref)
+    got = y.cpu().numpy()
+    assert not np.isnan(got).any() and _err(got, ref.numpy()) <= TOL
+
+
 def test_pools_match_torch():
     torch = _torch()
     x = torch.randn(2, 13, 13, 10)

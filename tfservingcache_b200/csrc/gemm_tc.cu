@@ -1,18 +1,22 @@
 // tcgen05 GEMM for the graph executor (conv-as-GEMM, transformer dense layers), sm_100a only:
 //
-//   C[M,N] = act(A[M,K] (row stride lda) * B[K,N] + bias[N] (+ R[M,N])),  fp32 in / out, 3xTF32 split (fp32-accurate)
+//   C[M,N] = act(A[M,K] * B[K,N] + bias[N] (+ R[M,N])),  fp32 in / out, 3xTF32 split (fp32-accurate)
 //
-// Activations are the MMA "A" operand (M = 128 rows per CTA), weights [K,N] row-major the "B" operand:
-//   * TMA lands the A tile [128 m][32 k] (K-major, SWIZZLE_128B) and the B tile [32 k][BN n] (MN-major tf32 ->
-//     SWIZZLE_128B_ATOM_32B, 3-D map {32 n, K, N/32}) in a 4-stage shared-memory ring.
-//   * converter warps 2..5 move the A tile into TMEM (lane = row m, column = k) as A_hi (raw fp32 bits; kind::tf32
-//     ignores the low 13 mantissa bits) and A_lo = A - trunc_tf32(A); warps 6..9 write B_lo = B - trunc_tf32(B) next
-//     to B_hi in the stage, so B' = [B_hi | B_lo] is one MN-major operand of N = 2*BN columns.
-//   * per 8-wide k step: MMA1 D[:, 0:2BN] += A_hi . B'  (hh | hl), MMA2 D[:, BN:2BN] += A_lo . B_hi (lh): the large
-//     term and the small corrections have separate TMEM accumulators (the tensor core's fp32 accumulate truncates).
+// Round 2: both MMA operands come from shared memory (SS mode) and the A tile can be gathered by the TMA unit itself.
+//   * A (activations) is K-major: TMA lands the tile [128 m][32 k] (SWIZZLE_128B) either from a row-major matrix (2-D tiled
+//     map: dense layers, 1x1 stride-1 convs) or -- IMPLICIT GEMM, no im2col buffer -- straight from the NHWC activation
+//     tensor with an im2col tensor map (cuTensorMapEncodeIm2col): the 128 rows are 128 consecutive output pixels, the 32
+//     columns are 32 channels of one filter tap (kh, kw); padding arrives as zeros, strided convs through the map's
+//     traversal stride. The raw fp32 bits are A_hi (kind::tf32 ignores the low 13 mantissa bits).
+//   * B (weights [K,N] row-major) is MN-major: TMA 3-D map {32 n, K, N/32} -> SWIZZLE_128B_ATOM_32B slabs.
+//   * 8 converter warps write A_lo = A - trunc_tf32(A) and B_lo = B - trunc_tf32(B) next to the TMA tiles, elementwise at
+//     the same (swizzled) offsets, so no layout knowledge is needed: B' = [B_hi | B_lo] is one operand of N = 2*BN.
+//     (Round 1 moved A through TMEM with tcgen05.st; the A-from-TMEM read costs ~64 clk per MMA and needed a second
+//     barrier pair.)
+//   * per 8-wide k step: MMA1 D[:, 0:2BN] += A_hi . B'  (hh | hl), MMA2 D[:, BN:2BN] += A_lo . B_hi (lh): the large term
+//     and the small corrections have separate TMEM accumulators (the tensor core's fp32 accumulate truncates).
 //   * epilogue: tcgen05.ld, C = hh + small + bias (+ residual), ReLU / GELU(erf) / tanh, row-contiguous stores.
-// One CTA per 128 x BN output tile over the whole K (no split-K): conv / transformer GEMMs have M in the hundreds to
-// tens of thousands. Same role split as dense_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, 8 converter/epilogue warps.
+// One CTA per 128 x BN output tile over the whole K. warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 converters + epilogue.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -30,43 +34,66 @@ extern std::atomic<int64_t> g_launches_nn;
 
 namespace gt {
 constexpr int BM = 128, BK = 32;
-constexpr int A_BYTES = BM * BK * 4;  // 16 KB
-constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;  // 16 KB per A tile (hi or lo)
 constexpr int THREADS = 320;
-constexpr uint32_t kAopCol = 256;     // TMEM: D at [0, 2*BN), A operand staging at [256 + cb*64, +64): hi 32 | lo 32
 }  // namespace gt
+
+// geometry of an implicit-GEMM conv (A tile = TMA im2col gather from the NHWC activations)
+struct ConvGeom {
+  int C, KW, OH, OW, stride, pad;
+};
 
 template <int BN>
 struct GtSmem {
+  static constexpr int STAGES = BN == 128 ? 3 : 4;
   static constexpr int SLABS = BN / 32;                 // 32-column slabs of the B tile
   static constexpr int KG_BYTES = 2 * SLABS * 512;      // one 4-row k group: hi slabs then lo slabs, 512 B each
   static constexpr int B_BYTES = (gt::BK / 4) * KG_BYTES;  // 8 k groups: 2*BN*32*4 bytes
-  static constexpr int STAGE_BYTES = gt::A_BYTES + B_BYTES;
-  static constexpr int TOTAL = gt::STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int STAGE_BYTES = 2 * gt::A_BYTES + B_BYTES;   // A_hi | A_lo | B'
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;              // D: [0, BN) main, [BN, 2BN) corrections (power of two >= 32)
 };
+
+__device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// TMA im2col gather: coordinates {c, w, h, n} of the base pixel (input space), offsets {kw, kh} of the filter tap
+__device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h, int n,
+                                                   uint16_t woff, uint16_t hoff) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(woff), "h"(hoff)
+      : "memory");
+}
 
 __device__ __forceinline__ float gelu_erf_tc(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN>
+template <int BN, bool IM2COL>
 __global__ void __launch_bounds__(gt::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
-               const float* __restrict__ bias, const float* __restrict__ R, float* __restrict__ C, int M, int N, int K, int act) {
+               const float* __restrict__ bias, const float* __restrict__ R, float* __restrict__ C, int M, int N, int K, int act,
+               ConvGeom cg) {
   using S = GtSmem<BN>;
-  constexpr int NS = gt::STAGES;
+  constexpr int NS = S::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * S::STAGE_BYTES);
-  uint64_t* full = bars;            // [NS] TMA landed A and B_hi
-  uint64_t* conv = bars + NS;       // [NS] converters published A (TMEM) and B_lo (smem)
+  uint64_t* full = bars;            // [NS] TMA landed A_hi and B_hi
+  uint64_t* conv = bars + NS;       // [NS] converters published A_lo and B_lo
   uint64_t* empty = bars + 2 * NS;  // [NS] MMAs finished reading the stage
-  uint64_t* cempty = bars + 3 * NS; // [2]  MMAs finished reading TMEM A buffer cb
-  uint64_t* accum_full = cempty + 2;
+  uint64_t* accum_full = bars + 3 * NS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * gt::BM, n0 = blockIdx.x * BN;
   const int n_kblocks = (K + gt::BK - 1) / gt::BK;
-  constexpr int TMEM_COLS = 512;
+  constexpr int TMEM_COLS = S::TMEM_COLS;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -75,8 +102,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         mbar_init(&conv[s], 8);
         mbar_init(&empty[s], 1);
       }
-      mbar_init(&cempty[0], 1);
-      mbar_init(&cempty[1], 1);
       mbar_init(accum_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
@@ -93,41 +118,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    int pn = 0, ph = 0, pw = 0;  // im2col: base pixel of the tile's first row, input space
+    if (IM2COL) {
+      const int per_img = cg.OH * cg.OW;
+      pn = m0 / per_img;
+      const int rem = m0 - pn * per_img;
+      ph = (rem / cg.OW) * cg.stride - cg.pad;
+      pw = (rem % cg.OW) * cg.stride - cg.pad;
+    }
     for (int kb = 0; kb < n_kblocks; ++kb) {
       const int s = kb % NS, it = kb / NS;
       if (lane == 0) {
         if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
         uint8_t* stage = smem + s * S::STAGE_BYTES;
         mbar_expect_tx(&full[s], gt::A_BYTES + BN * gt::BK * 4);
-        tma_load_2d(stage, &amap, &full[s], kb * gt::BK, m0);            // A: [128 m][32 k], 128 B rows, SW128
+        if (IM2COL) {
+          // k block kb = 32 channels [c0, c0+32) of filter tap (kh, kw); K is ordered (kh, kw, c) like the HWIO kernel
+          const int k0 = kb * gt::BK, tap = k0 / cg.C, c0 = k0 - tap * cg.C;
+          tma_load_im2col_4d(stage, &amap, &full[s], c0, pw, ph, pn, (uint16_t)(tap % cg.KW), (uint16_t)(tap / cg.KW));
+        } else {
+          tma_load_2d(stage, &amap, &full[s], kb * gt::BK, m0);          // A: [128 m][32 k], 128 B rows, SW128
+        }
 #pragma unroll
         for (int g = 0; g < gt::BK / 4; ++g)                              // B_hi: k group g -> slabs [0, SLABS) of the group
-          tma_load_3d(stage + gt::A_BYTES + g * S::KG_BYTES, &bmap, &full[s], 0, kb * gt::BK + g * 4, n0 / 32);
+          tma_load_3d(stage + 2 * gt::A_BYTES + g * S::KG_BYTES, &bmap, &full[s], 0, kb * gt::BK + g * 4, n0 / 32);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc1 = make_idesc_ts_b(2 * BN, 1);  // A_hi (TMEM) x [B_hi | B_lo] (MN-major)
-    constexpr uint32_t idesc2 = make_idesc_ts_b(BN, 1);      // A_lo (TMEM) x  B_hi
+    constexpr uint32_t idesc1 = make_idesc_ts_b(2 * BN, 1);  // A_hi (K-major smem) x [B_hi | B_lo] (MN-major)
+    constexpr uint32_t idesc2 = make_idesc_ts_b(BN, 1);      // A_lo x B_hi
     for (int kb = 0; kb < n_kblocks; ++kb) {
-      const int s = kb % NS, it = kb / NS, cb = kb & 1;
+      const int s = kb % NS, it = kb / NS;
       if (lane == 0) {
         mbar_wait(&conv[s], it & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t bsm = smem_u32(smem + s * S::STAGE_BYTES + gt::A_BYTES);
-        const uint32_t ahi = tmem_base + gt::kAopCol + (uint32_t)(cb * 64);
-        const uint32_t alo = ahi + 32;
+        const uint32_t ahi = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t alo = ahi + gt::A_BYTES;
+        const uint32_t bsm = ahi + 2 * gt::A_BYTES;
 #pragma unroll
         for (int k8 = 0; k8 < gt::BK / 8; ++k8) {
+          // A (K-major, SWIZZLE_128B): 8-row groups SBO = 1 KB apart, k advances 32 B inside the swizzle row.
           // B' (MN-major tf32, SWIZZLE_128B_BASE32B): atoms of 4 k rows x 128 B; slabs LBO = 512 B apart, consecutive
           // 4-row k groups SBO = KG_BYTES apart; one MMA (K = 8) spans two k groups
           const uint64_t b = make_desc(bsm + k8 * 2 * S::KG_BYTES, 512, S::KG_BYTES, 1);
-          umma_tf32_ts(tmem_base, ahi + k8 * 8, b, idesc1, (kb | k8) ? 1u : 0u);
-          umma_tf32_ts(tmem_base + BN, alo + k8 * 8, b, idesc2, 1u);
+          umma_tf32_ss(tmem_base, make_desc(ahi + k8 * 32, 16, 1024, 2), b, idesc1, (kb | k8) ? 1u : 0u);
+          umma_tf32_ss(tmem_base + BN, make_desc(alo + k8 * 32, 16, 1024, 2), b, idesc2, 1u);
         }
         umma_commit(&empty[s]);
-        umma_commit(&cempty[cb]);
       }
       __syncwarp();
     }
@@ -136,50 +175,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   } else {
     const int ct = threadIdx.x - 64;   // 0..255
     const int q = warp & 3;            // TMEM lane quarter of this warp
-    if (warp < 6) {
-      // ===================== A converters (warps 2..5): smem A tile -> TMEM A_hi / A_lo =====================
-      const int m = q * 32 + lane;     // row of the tile = TMEM lane
-      for (int kb = 0; kb < n_kblocks; ++kb) {
-        const int s = kb % NS, it = kb / NS, cb = kb & 1, cit = kb >> 1;
-        if (cit > 0) mbar_wait(&cempty[cb], (cit - 1) & 1);
-        mbar_wait(&full[s], it & 1);
-        const uint32_t arow = smem_u32(smem + s * S::STAGE_BYTES) + (uint32_t)(m * 128);
-        uint32_t hi[32], lo[32];
+    // ===================== converters (warps 2..9): X_lo = X - trunc_tf32(X), elementwise at the same offsets =========
+    for (int kb = 0; kb < n_kblocks; ++kb) {
+      const int s = kb % NS, it = kb / NS;
+      mbar_wait(&full[s], it & 1);     // the stage itself is free: the producer waited on empty[s] before refilling
+      const uint32_t ast = smem_u32(smem + s * S::STAGE_BYTES);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {  // 16-byte chunk c of row m sits at chunk (c ^ (m & 7)) (128-byte swizzle)
-          const float4 v = lds_f4(arow + (uint32_t)(((c ^ (m & 7)) << 4)));
-          hi[4 * c + 0] = __float_as_uint(v.x); lo[4 * c + 0] = __float_as_uint(tf32_lo(v.x));
-          hi[4 * c + 1] = __float_as_uint(v.y); lo[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
-          hi[4 * c + 2] = __float_as_uint(v.z); lo[4 * c + 2] = __float_as_uint(tf32_lo(v.z));
-          hi[4 * c + 3] = __float_as_uint(v.w); lo[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
-        }
-        const uint32_t aop = tmem_base + ((uint32_t)(q * 32) << 16) + gt::kAopCol + (uint32_t)(cb * 64);
-        tmem_st32(aop, hi);
-        tmem_st32(aop + 32, lo);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&conv[s]);
+      for (int i = 0; i < gt::A_BYTES / 16 / 256; ++i) {          // A tile: 1024 float4, 4 per thread
+        const uint32_t src = ast + (uint32_t)((ct + i * 256) * 16);
+        const float4 v = lds_f4(src);
+        sts_f4(src + gt::A_BYTES, make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)));
       }
-    } else {
-      // ===================== B converters (warps 6..9): B_lo = B - trunc_tf32(B), elementwise in place ==========
-      const int bt = ct - 128;         // 0..127
-      for (int kb = 0; kb < n_kblocks; ++kb) {
-        const int s = kb % NS, it = kb / NS;
-        mbar_wait(&full[s], it & 1);   // the stage itself is free: the producer waited on empty[s] before refilling
-        const uint32_t bsm = smem_u32(smem + s * S::STAGE_BYTES + gt::A_BYTES);
-        // hi part of k group g: bytes [g*KG, g*KG + SLABS*512); lo part right behind it
-        constexpr int F4_PER_GROUP = S::SLABS * 512 / 16;
-        for (int idx = bt; idx < (gt::BK / 4) * F4_PER_GROUP; idx += 128) {
-          const int g = idx / F4_PER_GROUP, o = idx - g * F4_PER_GROUP;
-          const uint32_t src = bsm + (uint32_t)(g * S::KG_BYTES + o * 16);
-          const float4 v = lds_f4(src);
-          sts_f4(src + S::SLABS * 512, make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)));
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&conv[s]);
+      const uint32_t bsm = ast + 2 * gt::A_BYTES;
+      // hi part of k group g: bytes [g*KG, g*KG + SLABS*512); lo part right behind it
+      constexpr int F4_PER_GROUP = S::SLABS * 512 / 16;
+      for (int idx = ct; idx < (gt::BK / 4) * F4_PER_GROUP; idx += 256) {
+        const int g = idx / F4_PER_GROUP, o = idx - g * F4_PER_GROUP;
+        const uint32_t src = bsm + (uint32_t)(g * S::KG_BYTES + o * 16);
+        const float4 v = lds_f4(src);
+        sts_f4(src + S::SLABS * 512, make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)));
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&conv[s]);
     }
     // ===================== epilogue: all 8 warps, 4 lane quarters x 2 column halves =====================
     mbar_wait(accum_full, 0);
@@ -256,28 +274,48 @@ bool gemm_tc_supported(const float* A, const float* B, const float* bias, const 
          (!bias || al16(bias)) && (!R || al16(R)) && tc_encode_fn() != nullptr;
 }
 
-template <int BN>
+template <int BN, bool IM2COL>
 static cudaError_t launch_gt(const CUtensorMap& am, const CUtensorMap& bm, const float* bias, const float* R, float* C, int M,
-                             int N, int K, int act, cudaStream_t s) {
+                             int N, int K, int act, const ConvGeom& cg, cudaStream_t s) {
   static bool attr[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtSmem<BN>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtSmem<BN>::TOTAL);
     if (e != cudaSuccess) return e;
     attr[dev & 63] = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + gt::BM - 1) / gt::BM);
-  gemm_tc_kernel<BN><<<grid, gt::THREADS, GtSmem<BN>::TOTAL, s>>>(am, bm, bias, R, C, M, N, K, act);
+  gemm_tc_kernel<BN, IM2COL><<<grid, gt::THREADS, GtSmem<BN>::TOTAL, s>>>(am, bm, bias, R, C, M, N, K, act, cg);
   g_launches_nn++;
   return cudaGetLastError();
+}
+
+static int pick_bn(int M, int N) {
+  if (N % 128 != 0 && N <= 128) return 64;
+  // small problems: 128 x 64 tiles double the CTA count (BERT's N = 768 projections: 48 -> 96 CTAs on 148 SMs)
+  const long tiles128 = (long)((N + 127) / 128) * ((M + gt::BM - 1) / gt::BM);
+  return tiles128 < 120 && N % 64 == 0 ? 64 : 128;
+}
+
+static bool weight_map(const float* B, int K, int N, int BN, CUtensorMap* bm) {
+  EncodeTiledFn enc = tc_encode_fn();
+  return cached_map({B, K, N, BN}, [&](CUtensorMap* m) {
+    const cuuint64_t gdim[3] = {32, (cuuint64_t)K, (cuuint64_t)(N / 32)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)N * 4, 128};
+    const cuuint32_t box[3] = {32, 4, (cuuint32_t)(BN / 32)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(B), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }, bm);
 }
 
 cudaError_t launch_gemm_tc(const float* A, const float* B, const float* bias, const float* R, float* C, int M, int N, int K,
                            int lda, int act, cudaStream_t s) {
   EncodeTiledFn enc = tc_encode_fn();
   if (!enc) return cudaErrorNotSupported;
-  const int BN = (N % 128 == 0 || N > 128) ? 128 : 64;
+  const int BN = pick_bn(M, N);
   CUtensorMap am, bm;
   if (!cached_map({A, M, K, lda}, [&](CUtensorMap* m) {
         const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
@@ -289,17 +327,60 @@ cudaError_t launch_gemm_tc(const float* A, const float* B, const float* bias, co
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
       }, &am))
     return cudaErrorInvalidValue;
-  if (!cached_map({B, K, N, BN}, [&](CUtensorMap* m) {
-        const cuuint64_t gdim[3] = {32, (cuuint64_t)K, (cuuint64_t)(N / 32)};
-        const cuuint64_t gstride[2] = {(cuuint64_t)N * 4, 128};
-        const cuuint32_t box[3] = {32, 4, (cuuint32_t)(BN / 32)};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(B), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-      }, &bm))
+  if (!weight_map(B, K, N, BN, &bm)) return cudaErrorInvalidValue;
+  const ConvGeom none{};
+  return BN == 128 ? launch_gt<128, false>(am, bm, bias, R, C, M, N, K, act, none, s)
+                   : launch_gt<64, false>(am, bm, bias, R, C, M, N, K, act, none, s);
+}
+
+// ---- implicit-GEMM convolution: NHWC activations x HWIO kernel, A tiles gathered by TMA im2col (no col buffer) ----
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn im2col_encode_fn() {
+  static EncodeIm2colFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<EncodeIm2colFn>(p);
+  }();
+  return fn;
+}
+
+bool conv_tc_supported(const float* x, const float* w, const float* bias, const float* R, const float* y, int Bn, int H, int W,
+                       int C, int KH, int KW, int stride, int pad, int OH, int OW, int N) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const long M = (long)Bn * OH * OW;
+  return C % 32 == 0 && N >= 64 && N % 32 == 0 && M >= 64 && KH >= 1 && KW >= 1 && KH <= 16 && KW <= 16 && stride >= 1 && stride <= 8 &&
+         pad >= 0 && pad < KH && pad < KW && H > 0 && W > 0 && al16(x) && al16(w) && al16(y) && (!bias || al16(bias)) &&
+         (!R || al16(R)) && tc_encode_fn() != nullptr && im2col_encode_fn() != nullptr;
+}
+
+cudaError_t launch_conv_tc(const float* x, const float* w, const float* bias, const float* R, float* y, int Bn, int H, int W, int C,
+                           int KH, int KW, int stride, int pad, int OH, int OW, int N, int act, cudaStream_t s) {
+  EncodeIm2colFn enc = im2col_encode_fn();
+  if (!enc) return cudaErrorNotSupported;
+  const int M = Bn * OH * OW, K = KH * KW * C;
+  const int BN = pick_bn(M, N);
+  CUtensorMap am, bm;
+  if (!cached_map({x, ((int64_t)Bn << 40) | ((int64_t)H << 20) | W, ((int64_t)C << 32) | (KH << 16) | KW, ((int64_t)stride << 8) | pad},
+                  [&](CUtensorMap* m) {
+        const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bn};
+        const cuuint64_t gstride[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+        // base pixels (top-left corner of the filter window, input space) range over [-pad, dim + pad - K] per axis,
+        // visited with the conv stride; tap offsets {kw, kh} are added per load
+        const int lower[2] = {-pad, -pad};
+        const int upper[2] = {pad - (KW - 1), pad - (KH - 1)};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstride, lower, upper, (cuuint32_t)gt::BK,
+                   (cuuint32_t)gt::BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      }, &am))
     return cudaErrorInvalidValue;
-  return BN == 128 ? launch_gt<128>(am, bm, bias, R, C, M, N, K, act, s) : launch_gt<64>(am, bm, bias, R, C, M, N, K, act, s);
+  if (!weight_map(w, K, N, BN, &bm)) return cudaErrorInvalidValue;
+  const ConvGeom cg{C, KW, OH, OW, stride, pad};
+  return BN == 128 ? launch_gt<128, true>(am, bm, bias, R, y, M, N, K, act, cg, s)
+                   : launch_gt<64, true>(am, bm, bias, R, y, M, N, K, act, cg, s);
 }
 
 }  // namespace tfsc

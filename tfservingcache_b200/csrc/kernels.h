@@ -65,6 +65,13 @@ struct CopySeg {
 };
 cudaError_t launch_copy_segments(const CopySeg* segs, int n, cudaStream_t s);
 
+// X4: implicit-GEMM convolution on tcgen05 (gemm_tc.cu): y[B,OH,OW,N] = act(conv(x[B,H,W,C], w[KH,KW,C,N]) + bias (+ R)); the A
+// tiles are gathered from the NHWC activations by TMA im2col tensor maps -- no patch matrix in HBM. C % 32 == 0, N % 32 == 0.
+bool conv_tc_supported(const float* x, const float* w, const float* bias, const float* R, const float* y, int Bn, int H, int W,
+                       int C, int KH, int KW, int stride, int pad, int OH, int OW, int N);
+cudaError_t launch_conv_tc(const float* x, const float* w, const float* bias, const float* R, float* y, int Bn, int H, int W, int C,
+                           int KH, int KW, int stride, int pad, int OH, int OW, int N, int act, cudaStream_t s);
+
 int64_t kernel_launch_count();
 
 }  // namespace tfsc

@@ -1,6 +1,7 @@
 #include "node.h"
 
 #include <chrono>
+#include <cstdlib>
 #include <set>
 
 #include "kernels.h"
@@ -575,7 +576,20 @@ size_t Node::model_ws_bytes(const ModelDesc& d) {
     size_t w = dense_workspace_bytes(kMaxRowsPerLaunch, L.in, L.out);
     if (w > m) m = w;
   }
+  for (auto& o : d.ops)  // graph bundles: plain dense heads (ResNet fc) run on the weight-streaming dense kernels
+    if (o.kind == OpKind::Dense) {
+      size_t w = dense_workspace_bytes(kMaxRowsPerLaunch, o.c, o.cout);
+      if (w > m) m = w;
+    }
   return m;
+}
+
+static bool conv_tc_enabled() {  // TFSC_CONV_TC=0: explicit im2col + GEMM (the round-1 path) for A/B comparisons
+  static bool v = [] {
+    const char* e = getenv("TFSC_CONV_TC");
+    return !e || atoi(e) != 0;
+  }();
+  return v;
 }
 
 cudaError_t Node::run_model(const DeviceModel& dm, const char* x, int64_t rows, char* y, char* scratch, void* ws,
@@ -601,7 +615,20 @@ cudaError_t Node::run_model(const DeviceModel& dm, const char* x, int64_t rows, 
         const float* bias = (const float*)(dm.dptr + o.b_off);
         const float* res = o.res == -100 ? nullptr : (const float*)buf(o.res);
         const int K = o.kh * o.kw * o.c;
+        if (o.kind == OpKind::Dense && !res && o.act <= 1 && (int)o.lda == K && B < 64) {
+          // a classifier head on a handful of rows is the tenant-MLP problem (HBM-bound weight streaming), not a GEMM tile
+          e = launch_dense(src, W, bias, dst, B, K, o.cout, o.act == 1, ws, ws_cap, st);
+          if (e != cudaSuccess) return e;
+          continue;
+        }
         const bool direct = o.kh == 1 && o.kw == 1 && o.stride == 1 && o.pad == 0;
+        if (o.kind == OpKind::Conv && !direct && conv_tc_enabled() &&
+            conv_tc_supported(src, W, bias, res, dst, B, o.h, o.w, o.c, o.kh, o.kw, o.stride, o.pad, o.oh, o.ow, o.cout)) {
+          // implicit GEMM: TMA im2col gathers the patch tiles straight from the NHWC activations (no col buffer)
+          e = launch_conv_tc(src, W, bias, res, dst, B, o.h, o.w, o.c, o.kh, o.kw, o.stride, o.pad, o.oh, o.ow, o.cout, o.act, st);
+          if (e != cudaSuccess) return e;
+          continue;
+        }
         const float* A = src;
         int lda = o.kind == OpKind::Dense ? (int)o.lda : K;  // Dense over a [S,H] source reads token 0 of every sequence
         if (!direct) {

@@ -1358,6 +1358,15 @@ int tfsc_k_gemm_tc(const float* a, const float* b, const float* bias, const floa
   cudaError_t e = launch_gemm_tc(a, b, bias, r, c, m, n, k, lda, act, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "gemm_tc: %s", cudaGetErrorString(e));
 }
+int tfsc_k_conv_tc(const float* x, const float* w, const float* bias, const float* r, float* y, int batch, int h, int wd, int c,
+                   int kh, int kw, int stride, int pad, int cout, int act, void* stream) {
+  if (int rc = check_device()) return rc;
+  const int oh = (h + 2 * pad - kh) / stride + 1, ow = (wd + 2 * pad - kw) / stride + 1;
+  if (!conv_tc_supported(x, w, bias, r, y, batch, h, wd, c, kh, kw, stride, pad, oh, ow, cout))
+    return fail(TFSC_E_INVALID, "conv_tc: unsupported shape/alignment (c %% 32 == 0, cout >= 64 and %% 32 == 0, batch*oh*ow >= 64, 16B-aligned)");
+  cudaError_t e = launch_conv_tc(x, w, bias, r, y, batch, h, wd, c, kh, kw, stride, pad, oh, ow, cout, act, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "conv_tc: %s", cudaGetErrorString(e));
+}
 int tfsc_k_im2col(const float* x, float* col, int batch, int h, int w, int c, int kh, int kw, int stride, int pad, int ldc,
                   void* stream) {
   if (int rc = check_device()) return rc;
