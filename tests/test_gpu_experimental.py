@@ -1,14 +1,14 @@
-"""-m gpu, opt-in (TFSC_TEST_EXPERIMENTAL=1): code paths that were written after the round's GPU budget was spent and have
-not run on a B200 yet. They are skipped in the default run so an unvalidated path cannot mask the validated suite; run
-them first thing in the next round:  TFSC_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q"""
+"""-m gpu: the dense-kernel variants and their programmatic-dependent-launch switch, each in its own process (TFSC_PDL /
+TFSC_DENSE_VARIANT are read once per process). Written at the end of round 1, validated on a B200 at the start of round 2
+(profiles/r2/dense_ab.jsonl): the cluster-pair kernel + PDL became the default for <= 8 rows; the other variants stay
+selectable for A/B runs, so they stay under test."""
 import os
 import subprocess
 import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("TFSC_TEST_EXPERIMENTAL") != "1", reason="opt-in: TFSC_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 PDL_SCRIPT = r"""

@@ -223,3 +223,20 @@ def test_bert_base_full_size_matches_oracle():
         y = srv.predict("m2", "1", ids)
     ref = models.graph_forward(oman, models.synth_graph_blob(oman, 1002), ids, np.float64)
     assert y.shape == (8, 2) and _err(y, ref) <= TOL
+
+
+@pytest.mark.parametrize("splits", ["2", "8"])
+def test_cluster_split_k_paths_of_the_graph_gemm(splits):
+    """The cluster split-K fold (DSMEM) is only chosen for small tile grids; force it for every GEMM / implicit conv case of
+    this file (TFSC_GEMM_SPLITK is read once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("TFSC_GEMM_SPLITK"):
+        pytest.skip("already inside the forced-split run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TFSC_GEMM_SPLITK=splits)
+    run = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                          "gemm_tc_matches or implicit_gemm or small_resnet or small_bert"], capture_output=True, text=True, timeout=900,
+                         env=env, cwd=root)
+    assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]

@@ -16,11 +16,15 @@
 //   * per 8-wide k step: MMA1 D[:, 0:2BN] += A_hi . B'  (hh | hl), MMA2 D[:, BN:2BN] += A_lo . B_hi (lh): the large term
 //     and the small corrections have separate TMEM accumulators (the tensor core's fp32 accumulate truncates).
 //   * epilogue: tcgen05.ld, C = hh + small + bias (+ residual), ReLU / GELU(erf) / tanh, row-contiguous stores.
-// One CTA per 128 x BN output tile over the whole K. warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 converters + epilogue.
+// One CTA per 128 x BN output tile; small grids (late ResNet stages: M = 392, K = 4608; BERT's K = 3072 projection) split K
+// over a thread-block cluster of 2 / 4 / 8 CTAs along grid.z: every CTA parks its partial tile in its own shared memory
+// and each CTA folds 128/S rows of the tile over distributed shared memory in fixed rank order (deterministic), then
+// applies bias / residual / activation. warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 converters + epilogue.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <functional>
 #include <mutex>
 #include <unordered_map>
@@ -92,8 +96,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * gt::BM, n0 = blockIdx.x * BN;
-  const int n_kblocks = (K + gt::BK - 1) / gt::BK;
+  // split-K: grid.z = cluster size S; this CTA (cluster rank = blockIdx.z) takes k blocks [kb0, kb0 + n_kblocks)
+  const int splits = (int)gridDim.z, split = (int)blockIdx.z;
+  const int total_kblocks = (K + gt::BK - 1) / gt::BK;
+  const int per_split = (total_kblocks + splits - 1) / splits;
+  const int kb0 = split * per_split;
+  const int n_kblocks = max(0, min(total_kblocks, kb0 + per_split) - kb0);
   constexpr int TMEM_COLS = S::TMEM_COLS;
+  constexpr int PSTRIDE = BN + 4;   // partial tile [128][BN + 4] fp32 (padded: conflict-free float4 stores, one row per lane)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -134,14 +144,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         mbar_expect_tx(&full[s], gt::A_BYTES + BN * gt::BK * 4);
         if (IM2COL) {
           // k block kb = 32 channels [c0, c0+32) of filter tap (kh, kw); K is ordered (kh, kw, c) like the HWIO kernel
-          const int k0 = kb * gt::BK, tap = k0 / cg.C, c0 = k0 - tap * cg.C;
+          const int k0 = (kb0 + kb) * gt::BK, tap = k0 / cg.C, c0 = k0 - tap * cg.C;
           tma_load_im2col_4d(stage, &amap, &full[s], c0, pw, ph, pn, (uint16_t)(tap % cg.KW), (uint16_t)(tap / cg.KW));
         } else {
-          tma_load_2d(stage, &amap, &full[s], kb * gt::BK, m0);          // A: [128 m][32 k], 128 B rows, SW128
+          tma_load_2d(stage, &amap, &full[s], (kb0 + kb) * gt::BK, m0);  // A: [128 m][32 k], 128 B rows, SW128
         }
 #pragma unroll
         for (int g = 0; g < gt::BK / 4; ++g)                              // B_hi: k group g -> slabs [0, SLABS) of the group
-          tma_load_3d(stage + 2 * gt::A_BYTES + g * S::KG_BYTES, &bmap, &full[s], 0, kb * gt::BK + g * 4, n0 / 32);
+          tma_load_3d(stage + 2 * gt::A_BYTES + g * S::KG_BYTES, &bmap, &full[s], 0, (kb0 + kb) * gt::BK + g * 4, n0 / 32);
       }
       __syncwarp();
     }
@@ -170,7 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       }
       __syncwarp();
     }
-    if (lane == 0) umma_commit(accum_full);
+    if (lane == 0 && n_kblocks > 0) umma_commit(accum_full);
     __syncwarp();
   } else {
     const int ct = threadIdx.x - 64;   // 0..255
@@ -200,17 +210,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       if (lane == 0) mbar_arrive(&conv[s]);
     }
     // ===================== epilogue: all 8 warps, 4 lane quarters x 2 column halves =====================
-    mbar_wait(accum_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (n_kblocks > 0) {
+      mbar_wait(accum_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     const int half = (warp - 2) >> 2;                  // warps 2..5 -> columns [0, BN/2), warps 6..9 -> [BN/2, BN)
     const int gm = m0 + q * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* part = reinterpret_cast<float*>(smem) + (size_t)(q * 32 + lane) * PSTRIDE;   // split-K: this thread's row of the partial
 #pragma unroll
     for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 16) {
       float hh[16], sm[16];
-      tmem_ld16(taddr + c, hh);
-      tmem_ld16(taddr + BN + c, sm);
-      if (gm < M) {
+      if (n_kblocks > 0) {
+        tmem_ld16(taddr + c, hh);
+        tmem_ld16(taddr + BN + c, sm);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hh[j] = sm[j] = 0.f;
+      }
+      if (splits > 1) {
+        // every MMA of this CTA has completed (accum_full), so the stages are idle: the partial tile overlays them
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(part + c + j) = make_float4(hh[j] + sm[j], hh[j + 1] + sm[j + 1], hh[j + 2] + sm[j + 2], hh[j + 3] + sm[j + 3]);
+      } else if (gm < M) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           const int gn = n0 + c + j;
@@ -236,6 +259,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  if (splits > 1) {
+    // ---- the K slices meet in distributed shared memory: rank r folds rows [r*128/S, (r+1)*128/S) of the tile ----
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // every CTA of the cluster parked its partial
+    const int rows_per = gt::BM / splits;
+    const uint32_t part_s = smem_u32(smem);
+    constexpr int V4 = BN / 4;
+    for (int idx = threadIdx.x; idx < rows_per * V4; idx += gt::THREADS) {
+      const int r = split * rows_per + idx / V4, c = (idx % V4) * 4;
+      const int gm = m0 + r, gn = n0 + c;
+      if (gm >= M || gn >= N) continue;
+      const uint32_t off = part_s + (uint32_t)((r * PSTRIDE + c) * 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s2 = 0; s2 < splits; ++s2) {                                   // fixed rank order: bit-reproducible
+        uint32_t raddr;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(off), "r"((uint32_t)s2));
+        float4 t;
+        asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(raddr) : "memory");
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+      }
+      if (bias) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + gn));
+        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      }
+      if (R) {
+        const float4 rv = __ldg(reinterpret_cast<const float4*>(R + (size_t)gm * N + gn));
+        v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+      }
+      if (act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      else if (act == 2) { v.x = gelu_erf_tc(v.x); v.y = gelu_erf_tc(v.y); v.z = gelu_erf_tc(v.z); v.w = gelu_erf_tc(v.w); }
+      else if (act == 3) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+      *reinterpret_cast<float4*>(C + (size_t)gm * N + gn) = v;
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // peers may still be reading this CTA's partial
+  }
 }
 
 // --------------------------------------------------------------------------------- host side ----
@@ -285,10 +344,35 @@ static cudaError_t launch_gt(const CUtensorMap& am, const CUtensorMap& bm, const
     if (e != cudaSuccess) return e;
     attr[dev & 63] = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + gt::BM - 1) / gt::BM);
-  gemm_tc_kernel<BN, IM2COL><<<grid, gt::THREADS, GtSmem<BN>::TOTAL, s>>>(am, bm, bias, R, C, M, N, K, act, cg);
+  const int tiles = ((N + BN - 1) / BN) * ((M + gt::BM - 1) / gt::BM);
+  const int kblocks = (K + gt::BK - 1) / gt::BK;
+  // split-K over a cluster when the tile grid alone leaves most of the 148 SMs idle and K is long enough to share
+  int splits = 1;
+  while (splits < 8 && tiles * splits * 2 <= 148 && kblocks / (splits * 2) >= 6) splits *= 2;
+  static const int force = [] {
+    const char* e = getenv("TFSC_GEMM_SPLITK");   // 0 = never split (A/B), 2 / 4 / 8 = force where K allows
+    return e ? atoi(e) : -1;
+  }();
+  if (force == 0) splits = 1;
+  else if (force > 0) {
+    splits = 1;
+    while (splits < force && splits < 8 && kblocks / (splits * 2) >= 1) splits *= 2;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((N + BN - 1) / BN, (M + gt::BM - 1) / gt::BM, splits);
+  cfg.blockDim = dim3(gt::THREADS);
+  cfg.dynamicSmemBytes = GtSmem<BN>::TOTAL;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = splits;
+  cfg.attrs = at;
+  cfg.numAttrs = splits > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, IM2COL>, am, bm, bias, R, C, M, N, K, act, cg);
   g_launches_nn++;
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 static int pick_bn(int M, int N) {

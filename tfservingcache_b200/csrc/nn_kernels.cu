@@ -176,13 +176,39 @@ im2col_nhwc_kernel(const float* __restrict__ x, float* __restrict__ col, int Bn,
   }
 }
 
+// Row-parallel version (round 2): a thread keeps its patch column kk = (kh, kw, c) for the whole kernel, so the 64-bit
+// div / mod chain of the kernel above runs once per thread instead of once per element; blockDim.y rows per iteration, the
+// row index decomposition is uniform per (block, y). Only convs that cannot take the implicit-GEMM path come here (the
+// ResNet stem: C = 3 is not a TMA row) -- for it the patch row is 7 runs of 21 contiguous floats, written coalesced.
+__global__ void __launch_bounds__(1024)
+im2col_rows_kernel(const float* __restrict__ x, float* __restrict__ col, int Bn, int H, int W, int C, int KH, int KW,
+                   int stride, int pad, int OH, int OW, int ldc) {
+  const int Kreal = KH * KW * C;
+  const int64_t rows = (int64_t)Bn * OH * OW;
+  for (int kk = threadIdx.x; kk < ldc; kk += blockDim.x) {
+    const bool real = kk < Kreal;
+    const int c = kk % C, kw = (kk / C) % KW, kh = kk / (C * KW);
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; row < rows; row += (int64_t)gridDim.x * blockDim.y) {
+      const int ow = (int)(row % OW);
+      const int64_t t = row / OW;
+      const int oh = (int)(t % OH), b = (int)(t / OH);
+      const int ih = oh * stride - pad + kh, iw = ow * stride - pad + kw;
+      float v = 0.f;
+      if (real && ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((int64_t)b * H + ih) * W + iw) * C + c);
+      col[row * ldc + kk] = v;
+    }
+  }
+}
+
 cudaError_t launch_im2col(const float* x, float* col, int Bn, int H, int W, int C, int KH, int KW, int stride, int pad,
                           int OH, int OW, int ldc, cudaStream_t s) {
-  const int64_t total = (int64_t)Bn * OH * OW * ldc;
-  if (total <= 0) return cudaSuccess;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  im2col_nhwc_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, col, Bn, H, W, C, KH, KW, stride, pad, OH, OW, ldc);
+  const int64_t rows = (int64_t)Bn * OH * OW;
+  if (rows <= 0 || ldc <= 0) return cudaSuccess;
+  const int bx = ldc >= 256 ? 256 : (ldc + 31) / 32 * 32;
+  const int by = 1024 / bx >= 1 ? (1024 / bx > 8 ? 8 : 1024 / bx) : 1;
+  int64_t blocks = (rows + by - 1) / by;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  im2col_rows_kernel<<<(unsigned)blocks, dim3(bx, by), 0, s>>>(x, col, Bn, H, W, C, KH, KW, stride, pad, OH, OW, ldc);
   g_launches_nn++;
   return cudaGetLastError();
 }
