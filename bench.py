@@ -666,7 +666,7 @@ def run_b200(args):
         from tools.traces import uniform_trace
         barrier()
         srv.set_max_resident(0, args.pressure_resident)
-        n_p = 3 * tick_global
+        n_p = 3 * args.tick      # per rank, whatever N is (the phase runs at PCIe speed: ~240 req/s per GPU)
         utrace = np.asarray(my_models, np.int64)[uniform_trace(len(my_models), n_p, seed=7 + rank)]   # this rank's own models
         sp0 = srv.stats()
         tp0 = time.time()

@@ -307,6 +307,9 @@ int tfsc_k_gemm_tc(const float* a, const float* b, const float* bias, const floa
  * c % 32 == 0, cout >= 64 and % 32 == 0, batch*OH*OW >= 64. act: 0 none, 1 relu, 2 gelu, 3 tanh. */
 int tfsc_k_conv_tc(const float* x, const float* w, const float* bias, const float* r, float* y, int batch, int h, int wd, int c,
                    int kh, int kw, int stride, int pad, int cout, int act, void* stream);
+/* debugging aid: with TFSC_GT_TRACE=1 in the environment, 16 clock64 stamps of CTA 0 of the most recent persistent tcgen05
+ * GEMM launch (entry, setup done, first TMA, first tile landed, converted, first MMA, per-tile commit / epilogue, exit) */
+int tfsc_debug_gemm_trace(long long* out16);
 /* col[(b*OH+oh)*OW+ow][(kh*KW+kw)*C+c] patch matrix with row stride ldc >= KH*KW*C (zero padded) */
 int tfsc_k_im2col(const float* x, float* col, int batch, int h, int w, int c, int kh, int kw, int stride, int pad, int ldc,
                   void* stream);

@@ -55,6 +55,7 @@ struct GtSmem {
   static constexpr int B_BYTES = (gt::BK / 4) * KG_BYTES;  // 8 k groups: 2*BN*32*4 bytes
   static constexpr int STAGE_BYTES = 2 * gt::A_BYTES + B_BYTES;   // A_hi | A_lo | B'
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int TOTAL_PERSIST = TOTAL + 4 * 32 * 36 * 4;   // + the epilogue's transpose staging (4 warps x 32 rows x 36 floats)
   static constexpr int TMEM_COLS = 2 * BN;              // D: [0, BN) main, [BN, 2BN) corrections (power of two >= 32)
 };
 
@@ -77,6 +78,27 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap*
 }
 
 __device__ __forceinline__ float gelu_erf_tc(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// activation selected at COMPILE time inside the store loops: with a run-time `act` the compiler if-converts the chain and
+// every element pays for erff and tanhf (~200 instructions per float4) whatever the activation is -- the timeline showed the
+// epilogue store phase at ~300 clk per 512-byte store because of it
+template <int ACT>
+__device__ __forceinline__ float4 apply_act(float4 v);
+// run-time activation with REAL branches (noinline bodies cannot be if-converted into the caller's store loop)
+__device__ __noinline__ float4 act_gelu4(float4 v) { return make_float4(gelu_erf_tc(v.x), gelu_erf_tc(v.y), gelu_erf_tc(v.z), gelu_erf_tc(v.w)); }
+__device__ __noinline__ float4 act_tanh4(float4 v) { return make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w)); }
+__device__ __forceinline__ float4 apply_act_rt(float4 v, int act) {
+  if (act == 1) return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+  if (act == 2) return act_gelu4(v);
+  if (act == 3) return act_tanh4(v);
+  return v;
+}
+template <int ACT>
+__device__ __forceinline__ float4 apply_act(float4 v) {
+  if (ACT == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  else if (ACT == 2) { v.x = gelu_erf_tc(v.x); v.y = gelu_erf_tc(v.y); v.z = gelu_erf_tc(v.z); v.w = gelu_erf_tc(v.w); }
+  else if (ACT == 3) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+  return v;
+}
 
 template <int BN, bool IM2COL>
 __global__ void __launch_bounds__(gt::THREADS, 1)
@@ -247,9 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
             const float4 rv = __ldg(reinterpret_cast<const float4*>(R + (size_t)gm * N + gn));
             v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
           }
-          if (act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          else if (act == 2) { v.x = gelu_erf_tc(v.x); v.y = gelu_erf_tc(v.y); v.z = gelu_erf_tc(v.z); v.w = gelu_erf_tc(v.w); }
-          else if (act == 3) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+          v = apply_act_rt(v, act);
           *reinterpret_cast<float4*>(C + (size_t)gm * N + gn) = v;
         }
       }
@@ -287,14 +307,295 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         const float4 rv = __ldg(reinterpret_cast<const float4*>(R + (size_t)gm * N + gn));
         v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
       }
-      if (act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      else if (act == 2) { v.x = gelu_erf_tc(v.x); v.y = gelu_erf_tc(v.y); v.z = gelu_erf_tc(v.z); v.w = gelu_erf_tc(v.w); }
-      else if (act == 3) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+      v = apply_act_rt(v, act);
       *reinterpret_cast<float4*>(C + (size_t)gm * N + gn) = v;
     }
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // peers may still be reading this CTA's partial
   }
+}
+
+// ------------------------------------------------------------------------------- persistent variant ----
+// One CTA per SM walks the output tiles (tile = blockIdx.x + i * gridDim.x). Against the kernel above it pays the TMEM
+// allocation, barrier setup and descriptor prefetch once, keeps the TMA ring full across tile boundaries, and overlaps the
+// epilogue of tile i (4 dedicated warps, tcgen05.ld -> bias / residual / activation -> global) with the main loop of tile
+// i+1 through two TMEM accumulators. The graph models are made of many small GEMMs (ResNet-50: 53 convs, K = 64..4608): with
+// one tile per CTA the fixed per-tile cost (~6 us) was several times the MMA time of the small-K layers.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 converters (A_lo / B_lo), warps 10..13 epilogue.
+namespace gt {
+constexpr int P_THREADS = 64 + 256 + 128;
+}
+
+#define GT_TRACE(slot) do { if (trace && blockIdx.x == 0) trace[slot] = clock64(); } while (0)
+// epilogue of one tile for one epilogue warp (persistent kernel): TMEM -> staging rows -> coalesced stores, see the kernel
+template <int BN, int ACT>
+__device__ __forceinline__ void persist_epilogue_tile(uint32_t taddr, uint32_t stg_s, const float* __restrict__ bias,
+                                                      const float* __restrict__ R, float* __restrict__ C, int M, int N, int m0, int n0,
+                                                      int q, int lane, int prow, int pcol, long long* __restrict__ trace, int i, int warp) {
+  constexpr int EST = 36;
+      // bias of every chunk up front: its L2 latency must not sit between the TMEM loads and the stores of a chunk
+      float4 bvs[BN / 32];
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        const int gnb = n0 + cc * 32 + pcol;
+        bvs[cc] = (bias && gnb < N) ? __ldg(reinterpret_cast<const float4*>(bias + gnb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        const int c = cc * 32;
+        const int gn = n0 + c + pcol;
+        const float4 bv = bvs[cc];
+        {
+          uint32_t hh[32], sm[32];
+          tmem_ld32_nowait(taddr + c, hh);            // both loads in flight, one wait
+          tmem_ld32_nowait(taddr + BN + c, sm);
+          tmem_wait_ld();
+          if (i == 0 && cc == 0 && warp == 10 && lane == 0) GT_TRACE(13);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            sts_f4(stg_s + (uint32_t)((lane * EST + j) * 4),
+                   make_float4(__uint_as_float(hh[j]) + __uint_as_float(sm[j]), __uint_as_float(hh[j + 1]) + __uint_as_float(sm[j + 1]),
+                               __uint_as_float(hh[j + 2]) + __uint_as_float(sm[j + 2]), __uint_as_float(hh[j + 3]) + __uint_as_float(sm[j + 3])));
+        }
+        __syncwarp();
+        if (i == 0 && cc == 0 && warp == 10 && lane == 0) GT_TRACE(14);
+#pragma unroll
+        for (int r4 = 0; r4 < 32; r4 += 4) {
+          const int row = r4 + prow, gm = m0 + q * 32 + row;
+          float4 v = lds_f4(stg_s + (uint32_t)((row * EST + pcol) * 4));
+          if (gm < M && gn < N) {
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            if (R) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(R + (size_t)gm * N + gn));
+              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+            }
+            v = apply_act<ACT>(v);
+            *reinterpret_cast<float4*>(C + (size_t)gm * N + gn) = v;
+          }
+        }
+        __syncwarp();   // the staging rows are rewritten by the next chunk
+        if (i == 0 && cc == 0 && warp == 10 && lane == 0) GT_TRACE(15);
+      }
+}
+
+// optional timeline of CTA 0 (TFSC_GT_TRACE=1: the launcher passes a device buffer, tfsc_debug_gemm_trace reads it back)
+
+template <int BN, bool IM2COL>
+__global__ void __launch_bounds__(gt::P_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
+                       const float* __restrict__ bias, const float* __restrict__ R, float* __restrict__ C, int M, int N, int K,
+                       int act, ConvGeom cg, int tiles_n, int tiles_total, long long* __restrict__ trace) {
+  using S = GtSmem<BN>;
+  constexpr int NS = S::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * S::STAGE_BYTES);
+  uint64_t* full = bars;                 // [NS] TMA landed A_hi and B_hi
+  uint64_t* conv = bars + NS;            // [NS] converters published A_lo and B_lo
+  uint64_t* empty = bars + 2 * NS;       // [NS] MMAs finished reading the stage
+  uint64_t* accum_full = bars + 3 * NS;  // [2]  all MMAs of a tile have completed into accumulator ab
+  uint64_t* accum_empty = accum_full + 2;  // [2] the epilogue has read accumulator ab
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kblocks = (K + gt::BK - 1) / gt::BK;
+  constexpr int TMEM_COLS = 4 * BN;      // two accumulators of 2*BN columns (512 for BN = 128: the whole TMEM)
+  if (threadIdx.x == 0) GT_TRACE(0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < NS; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&conv[s], 8);
+        mbar_init(&empty[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&accum_full[a], 1);
+        mbar_init(&accum_empty[a], 4);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap) : "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) GT_TRACE(1);
+  // programmatic dependent launch: the next kernel of the stream may start its own setup / weight prefetch on SMs this grid
+  // has left; everything that depends on the PREVIOUS kernel (A tiles, residual, C) is touched only after griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == 0) {
+    // ===================== TMA producer: the ring does not drain at tile boundaries =====================
+    int g = 0;  // k blocks issued so far by this CTA (all tiles)
+    bool waited = false;
+    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * gt::BM, n0 = (tile % tiles_n) * BN;
+      int pn = 0, ph = 0, pw = 0;
+      if (IM2COL) {
+        const int per_img = cg.OH * cg.OW;
+        pn = m0 / per_img;
+        const int rem = m0 - pn * per_img;
+        ph = (rem / cg.OW) * cg.stride - cg.pad;
+        pw = (rem % cg.OW) * cg.stride - cg.pad;
+      }
+      auto load_a = [&](int kb, int s) {
+        uint8_t* stage = smem + s * S::STAGE_BYTES;
+        if (IM2COL) {
+          const int k0 = kb * gt::BK, tap = k0 / cg.C, c0 = k0 - tap * cg.C;
+          tma_load_im2col_4d(stage, &amap, &full[s], c0, pw, ph, pn, (uint16_t)(tap % cg.KW), (uint16_t)(tap / cg.KW));
+        } else {
+          tma_load_2d(stage, &amap, &full[s], kb * gt::BK, m0);
+        }
+      };
+      auto load_b = [&](int kb, int s) {
+        uint8_t* stage = smem + s * S::STAGE_BYTES;
+#pragma unroll
+        for (int gq = 0; gq < gt::BK / 4; ++gq)
+          tma_load_3d(stage + 2 * gt::A_BYTES + gq * S::KG_BYTES, &bmap, &full[s], 0, kb * gt::BK + gq * 4, n0 / 32);
+      };
+      int kb = 0;
+      if (!waited) {
+        // first stages of the first tile: the WEIGHT tiles never depend on the previous kernel -> in flight before the wait
+        const int pre = n_kblocks < NS ? n_kblocks : NS;
+        if (lane == 0) {
+          GT_TRACE(2);
+          for (int p = 0; p < pre; ++p) {
+            mbar_expect_tx(&full[p], gt::A_BYTES + BN * gt::BK * 4);
+            load_b(p, p);
+          }
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (lane == 0)
+          for (int p = 0; p < pre; ++p) load_a(p, p);
+        __syncwarp();
+        waited = true;
+        kb = pre;
+        g = pre;
+      }
+      for (; kb < n_kblocks; ++kb, ++g) {
+        const int s = g % NS, it = g / NS;
+        if (lane == 0) {
+          if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+          mbar_expect_tx(&full[s], gt::A_BYTES + BN * gt::BK * 4);
+          load_a(kb, s);
+          load_b(kb, s);
+        }
+        __syncwarp();
+      }
+    }
+    if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc1 = make_idesc_ts_b(2 * BN, 1);
+    constexpr uint32_t idesc2 = make_idesc_ts_b(BN, 1);
+    int g = 0, i = 0;
+    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++i) {
+      const int ab = i & 1, n = i >> 1;
+      const uint32_t dacc = tmem_base + (uint32_t)(ab * 2 * BN);
+      if (lane == 0 && n > 0) {
+        mbar_wait(&accum_empty[ab], (n - 1) & 1);   // the epilogue drained this accumulator (tile i - 2)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      for (int kb = 0; kb < n_kblocks; ++kb, ++g) {
+        const int s = g % NS, it = g / NS;
+        if (lane == 0) {
+          mbar_wait(&conv[s], it & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (g == 0) GT_TRACE(5);
+          const uint32_t ahi = smem_u32(smem + s * S::STAGE_BYTES);
+          const uint32_t alo = ahi + gt::A_BYTES;
+          const uint32_t bsm = ahi + 2 * gt::A_BYTES;
+#pragma unroll
+          for (int k8 = 0; k8 < gt::BK / 8; ++k8) {
+            const uint64_t b = make_desc(bsm + k8 * 2 * S::KG_BYTES, 512, S::KG_BYTES, 1);
+            umma_tf32_ss(dacc, make_desc(ahi + k8 * 32, 16, 1024, 2), b, idesc1, (kb | k8) ? 1u : 0u);
+            umma_tf32_ss(dacc + BN, make_desc(alo + k8 * 32, 16, 1024, 2), b, idesc2, 1u);
+          }
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        umma_commit(&accum_full[ab]);
+        if (i < 2) GT_TRACE(6 + 3 * i);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 10) {
+    // ===================== converters (warps 2..9) =====================
+    const int ct = threadIdx.x - 64;   // 0..255
+    int g = 0;
+    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+      for (int kb = 0; kb < n_kblocks; ++kb, ++g) {
+        const int s = g % NS, it = g / NS;
+        mbar_wait(&full[s], it & 1);
+        if (g == 0 && ct == 0) GT_TRACE(3);
+        const uint32_t ast = smem_u32(smem + s * S::STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < gt::A_BYTES / 16 / 256; ++j) {
+          const uint32_t src = ast + (uint32_t)((ct + j * 256) * 16);
+          const float4 v = lds_f4(src);
+          sts_f4(src + gt::A_BYTES, make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)));
+        }
+        const uint32_t bsm = ast + 2 * gt::A_BYTES;
+        constexpr int F4_PER_GROUP = S::SLABS * 512 / 16;
+        for (int idx = ct; idx < (gt::BK / 4) * F4_PER_GROUP; idx += 256) {
+          const int gq = idx / F4_PER_GROUP, o = idx - gq * F4_PER_GROUP;
+          const uint32_t src = bsm + (uint32_t)(gq * S::KG_BYTES + o * 16);
+          const float4 v = lds_f4(src);
+          sts_f4(src + S::SLABS * 512, make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[s]);
+        if (g == 0 && ct == 0) GT_TRACE(4);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 10..13), TMEM lane quarter = warp % 4 =====================
+    // A thread owns one accumulator row in TMEM, but 16-byte stores from 32 different rows are 32 half-filled sectors and
+    // the per-row bias / residual loads sat on the critical path (timeline: 7.7k clk per 128 x 64 tile against a 2.6k clk
+    // main loop). So the tile is transposed through shared memory in 32-column chunks: phase A thread = row (tcgen05.ld ->
+    // padded staging rows, conflict-free float4 stores), phase B 8 lanes = one 128-byte row segment (bias / residual /
+    // activation, full-sector coalesced loads and stores). A warp only ever reads back the 32 rows it staged itself.
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // C / R may be buffers the previous kernel of the stream still uses
+    const int q = warp & 3;
+    constexpr int EST = 36;                                       // staging row stride in floats (32 + 4 pad)
+    float* stg = reinterpret_cast<float*>(smem + NS * S::STAGE_BYTES + 256) + (size_t)(warp - 10) * 32 * EST;
+    const uint32_t stg_s = smem_u32(stg);
+    const int prow = lane >> 3, pcol = (lane & 7) * 4;            // phase B: row within a group of 4, column within the chunk
+    int i = 0;
+    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++i) {
+      const int ab = i & 1, n = i >> 1;
+      const int m0 = (tile / tiles_n) * gt::BM, n0 = (tile % tiles_n) * BN;
+      mbar_wait(&accum_full[ab], n & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (i < 2 && warp == 10 && lane == 0) GT_TRACE(7 + 3 * i);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * BN);
+      switch (act) {   // uniform: one instantiation of the tile epilogue per activation
+        case 1: persist_epilogue_tile<BN, 1>(taddr, stg_s, bias, R, C, M, N, m0, n0, q, lane, prow, pcol, trace, i, warp); break;
+        case 2: persist_epilogue_tile<BN, 2>(taddr, stg_s, bias, R, C, M, N, m0, n0, q, lane, prow, pcol, trace, i, warp); break;
+        case 3: persist_epilogue_tile<BN, 3>(taddr, stg_s, bias, R, C, M, N, m0, n0, q, lane, prow, pcol, trace, i, warp); break;
+        default: persist_epilogue_tile<BN, 0>(taddr, stg_s, bias, R, C, M, N, m0, n0, q, lane, prow, pcol, trace, i, warp); break;
+      }
+      // the accumulator may be overwritten once every epilogue warp has pulled its rows out of TMEM
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&accum_empty[ab]);
+      if (i < 2 && warp == 10 && lane == 0) GT_TRACE(8 + 3 * i);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  if (threadIdx.x == 0) GT_TRACE(12);
 }
 
 // --------------------------------------------------------------------------------- host side ----
@@ -333,6 +634,21 @@ bool gemm_tc_supported(const float* A, const float* B, const float* bias, const 
          (!bias || al16(bias)) && (!R || al16(R)) && tc_encode_fn() != nullptr;
 }
 
+static long long* gt_trace_buffer() {  // TFSC_GT_TRACE=1: 16 clock64 stamps of CTA 0 of the most recent persistent launch
+  static long long* buf = [] {
+    const char* e = getenv("TFSC_GT_TRACE");
+    long long* p = nullptr;
+    if (e && atoi(e) != 0 && cudaMalloc(&p, 16 * sizeof(long long)) == cudaSuccess) cudaMemset(p, 0, 16 * sizeof(long long));
+    return p;
+  }();
+  return buf;
+}
+int gemm_trace_read(long long* out16) {
+  long long* p = gt_trace_buffer();
+  if (!p) return -1;
+  return cudaMemcpy(out16, p, 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+
 template <int BN, bool IM2COL>
 static cudaError_t launch_gt(const CUtensorMap& am, const CUtensorMap& bm, const float* bias, const float* R, float* C, int M,
                              int N, int K, int act, const ConvGeom& cg, cudaStream_t s) {
@@ -357,6 +673,40 @@ static cudaError_t launch_gt(const CUtensorMap& am, const CUtensorMap& bm, const
   else if (force > 0) {
     splits = 1;
     while (splits < force && splits < 8 && kblocks / (splits * 2) >= 1) splits *= 2;
+  }
+  static const bool persist = [] {
+    const char* e = getenv("TFSC_GEMM_PERSIST");   // 0 = one tile per CTA (the non-persistent kernel), for A/B runs
+    return !e || atoi(e) != 0;
+  }();
+  if (splits == 1 && persist) {
+    static bool pattr[64] = {};
+    static int sms[64] = {};
+    if (!pattr[dev & 63]) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtSmem<BN>::TOTAL_PERSIST);
+      if (e != cudaSuccess) return e;
+      if (cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev & 63] <= 0) sms[dev & 63] = 148;
+      pattr[dev & 63] = true;
+    }
+    const int tiles_n = (N + BN - 1) / BN;
+    const int grid = tiles < sms[dev & 63] ? tiles : sms[dev & 63];
+    static const bool pdl = [] {
+      const char* e = getenv("TFSC_PDL");
+      return !e || atoi(e) != 0;
+    }();
+    cudaLaunchConfig_t pc = {};
+    pc.gridDim = dim3(grid);
+    pc.blockDim = dim3(gt::P_THREADS);
+    pc.dynamicSmemBytes = GtSmem<BN>::TOTAL_PERSIST;
+    pc.stream = s;
+    cudaLaunchAttribute pa[1];
+    pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pa[0].val.programmaticStreamSerializationAllowed = 1;
+    pc.attrs = pa;
+    pc.numAttrs = pdl ? 1 : 0;
+    cudaError_t pe = cudaLaunchKernelEx(&pc, gemm_tc_persist_kernel<BN, IM2COL>, am, bm, bias, R, C, M, N, K, act, cg, tiles_n, tiles,
+                                        gt_trace_buffer());
+    g_launches_nn++;
+    return pe != cudaSuccess ? pe : cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((N + BN - 1) / BN, (M + gt::BM - 1) / gt::BM, splits);

@@ -72,6 +72,8 @@ bool conv_tc_supported(const float* x, const float* w, const float* bias, const 
 cudaError_t launch_conv_tc(const float* x, const float* w, const float* bias, const float* R, float* y, int Bn, int H, int W, int C,
                            int KH, int KW, int stride, int pad, int OH, int OW, int N, int act, cudaStream_t s);
 
+int gemm_trace_read(long long* out16);  // debugging aid (TFSC_GT_TRACE=1): clock64 timeline of CTA 0 of the last persistent GEMM
+
 int64_t kernel_launch_count();
 
 }  // namespace tfsc

@@ -1367,6 +1367,7 @@ int tfsc_k_conv_tc(const float* x, const float* w, const float* bias, const floa
   cudaError_t e = launch_conv_tc(x, w, bias, r, y, batch, h, wd, c, kh, kw, stride, pad, oh, ow, cout, act, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : fail(TFSC_E_INTERNAL, "conv_tc: %s", cudaGetErrorString(e));
 }
+int tfsc_debug_gemm_trace(long long* out16) { return gemm_trace_read(out16) == 0 ? 0 : fail(TFSC_E_INVALID, "set TFSC_GT_TRACE=1"); }
 int tfsc_k_im2col(const float* x, float* col, int batch, int h, int w, int c, int kh, int kw, int stride, int pad, int ldc,
                   void* stream) {
   if (int rc = check_device()) return rc;
