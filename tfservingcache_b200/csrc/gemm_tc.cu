@@ -147,6 +147,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: successors may begin their setup; this kernel (split-K path, few CTAs) simply waits for its
+  // predecessor here -- its own setup above already ran under the predecessor's tail
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -713,13 +717,26 @@ static cudaError_t launch_gt(const CUtensorMap& am, const CUtensorMap& bm, const
   cfg.blockDim = dim3(gt::THREADS);
   cfg.dynamicSmemBytes = GtSmem<BN>::TOTAL;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 1;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = splits;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (splits > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 1;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = splits;
+    ++na;
+  }
+  static const bool pdl2 = [] {
+    const char* e = getenv("TFSC_PDL");
+    return !e || atoi(e) != 0;
+  }();
+  if (pdl2) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = splits > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, IM2COL>, am, bm, bias, R, C, M, N, K, act, cg);
   g_launches_nn++;
   return e != cudaSuccess ? e : cudaGetLastError();

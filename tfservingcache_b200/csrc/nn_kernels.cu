@@ -183,6 +183,7 @@ im2col_nhwc_kernel(const float* __restrict__ x, float* __restrict__ col, int Bn,
 __global__ void __launch_bounds__(1024)
 im2col_rows_kernel(const float* __restrict__ x, float* __restrict__ col, int Bn, int H, int W, int C, int KH, int KW,
                    int stride, int pad, int OH, int OW, int ldc) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a tcgen05 GEMM that follows may start its setup + weight prefetch now (it waits for this grid before touching activations)
   const int Kreal = KH * KW * C;
   const int64_t rows = (int64_t)Bn * OH * OW;
   for (int kk = threadIdx.x; kk < ldc; kk += blockDim.x) {
@@ -217,6 +218,7 @@ cudaError_t launch_im2col(const float* x, float* col, int Bn, int H, int W, int 
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Bn, int H, int W, int C, int KH, int KW, int stride,
                     int pad, int OH, int OW) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a tcgen05 GEMM that follows may start its setup + weight prefetch now (it waits for this grid before touching activations)
   const int64_t total = (int64_t)Bn * OH * OW * C;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C);
@@ -245,6 +247,7 @@ cudaError_t launch_maxpool(const float* x, float* y, int Bn, int H, int W, int C
 // y[b][c] = mean over H*W of x[b][h][w][c]; sequential fp32 sum per (b,c): deterministic
 __global__ void __launch_bounds__(256)
 avgpool_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Bn, int HW, int C) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a tcgen05 GEMM that follows may start its setup + weight prefetch now (it waits for this grid before touching activations)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Bn * C) return;
   const int c = idx % C, b = idx / C;
@@ -294,6 +297,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res, con
                  const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int S, int H,
                  int vocab, float eps) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a tcgen05 GEMM that follows may start its setup + weight prefetch now (it waits for this grid before touching activations)
   __shared__ float2 sh[8];
   extern __shared__ float row[];
   const int token = blockIdx.x;
@@ -401,6 +405,7 @@ attention_kernel(const float* __restrict__ qkv, const int* __restrict__ ids, flo
 template <int KPL>
 __global__ void __launch_bounds__(128)
 attention_tile_kernel(const float* __restrict__ qkv, const int* __restrict__ ids, float* __restrict__ ctx, int S, int H, int heads) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a tcgen05 GEMM that follows may start its setup + weight prefetch now (it waits for this grid before touching activations)
   extern __shared__ __align__(16) float sm[];
   constexpr int SP = 32 * KPL;           // padded key count
   const int d = H / heads, ds = d + 4;   // d % 4 == 0
