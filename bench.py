@@ -293,7 +293,12 @@ class NvmlSampler:
                 sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
                 rs = int(reasons_fn(self.h)) if reasons_fn else 0
-                self.rows.append((time.time(), sm, pw, rs))
+                try:
+                    mem = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM)
+                    temp = nv.nvmlDeviceGetTemperature(self.h, nv.NVML_TEMPERATURE_GPU)
+                except Exception:
+                    mem, temp = -1, -1
+                self.rows.append((time.time(), sm, pw, rs, mem, temp))
             except Exception:
                 pass
             time.sleep(self.period_s)
@@ -311,6 +316,7 @@ class NvmlSampler:
             mask |= r[3]
         return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_min_mhz": float(min(r[1] for r in rows)),
                 "sm_max_mhz": float(self.max_sm), "power_w": round(float(np.median([r[2] for r in rows])), 1),
+                "mem_mhz": float(np.median([r[4] for r in rows])), "temp_c": float(np.median([r[5] for r in rows])),
                 "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(rows)}
 
 
