@@ -393,9 +393,16 @@ def graph_model_speed(kind, steps=30):
             "note": "fp32 in/out, 3xTF32 tcgen05 GEMMs; device-resident inputs, one model, CUDA events"}
 
 
+def _phase(rank, t0, name):
+    """progress marker on stderr (rank 0): where the time of a run goes, and where a hang sits"""
+    if rank == 0:
+        print(f"[bench +{time.time() - t0:6.1f}s] {name}", file=sys.stderr, flush=True)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
+    t_start = time.time()
 
     import tfservingcache_b200 as t
     from tfservingcache_b200 import _lib
@@ -450,6 +457,7 @@ def run_b200(args):
         n_slots = max(512, (2 * args.tick * max(inb, outb) + win_slot - 1) // win_slot + 8)
         cfg.update({"cluster.rank": rank, "cluster.endpoints": [os.path.join(sock_dir, f"r{r}.sock") for r in range(world)],
                     "cluster.slotBytes": win_slot, "cluster.windowSlots": int(n_slots), "proxy.grpcTimeout": 60.0})
+    _phase(rank, t_start, "workload built")
     srv = t.Server(cfg)
 
     # page every model this rank owns into HBM once (cold loads are not part of the steady-state metric;
@@ -458,6 +466,7 @@ def run_b200(args):
     for m in my_models:
         srv.ensure(0, f"m{m}", 1)
     load_s = time.time() - t_load
+    _phase(rank, t_start, f"shard resident ({len(my_models)} models, {load_s:.1f} s)")
 
     # a dedicated non-default stream: handle 0 (the legacy default stream) means "the node's own compute
     # stream" to tfsc_predict_device, and the CUDA events below must sit on the stream the kernels run on
@@ -486,10 +495,11 @@ def run_b200(args):
         assert args.tick * inb <= y_base and args.tick * outb <= my_win_bytes - y_base
         _lib.check(_lib.lib.tfsc_device_memcpy(my_win, x_dev.data_ptr(), min(args.tick * inb, x_dev.numel() * 4)))
         barrier()
-        for p in range(world):
-            if p != rank:
-                pwin[p] = srv.fwd_peer_window(p)[0]
+        for d in range(1, world):                 # ring schedule: at step d every rank dials a different peer
+            p = (rank + d) % world
+            pwin[p] = srv.fwd_peer_window(p)[0]
         barrier()
+        _phase(rank, t_start, "peer windows mapped")
 
     # the request trace of every value-region step is grouped before the clock starts: the timed loop is route ->
     # ensure-resident -> gather -> predict launches -> scatter only, not numpy bookkeeping of the synthetic trace
@@ -581,6 +591,7 @@ def run_b200(args):
     launches = lib.tfsc_kernel_launches() - launches0
     st1 = srv.stats()
 
+    _phase(rank, t_start, "value region done")
     # ---- e2e: host buffers through the C ABI, closed-loop clients ----------------------------------------------
     lg = C.CDLL(os.path.join(ROOT, "tools", "libtfsc_loadgen.so"))
     lg.tfsc_loadgen_run.restype = C.c_int64
@@ -647,6 +658,7 @@ def run_b200(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return [float(v) for v in tt]
 
+    _phase(rank, t_start, "e2e region done")
     # ---- latency-bounded throughput: closed-loop client sweep (north_star: cache-hit p50 < 5 ms) -----------------
     sweep, light = [], None
     if not args.skip_e2e and not args.no_extras:
@@ -666,6 +678,7 @@ def run_b200(args):
     ok = [p for p in sweep if p["p50_ms"] < 5.0]
     qps_at_p50_5ms = max(ok, key=lambda p: p["qps"]) if ok else None
 
+    _phase(rank, t_start, "client sweep done")
     # ---- cache under pressure: resident cap below the working set, uniform storm (configs[4]) ---------------------
     pressure = None
     if not args.skip_e2e and not args.no_extras and len(my_models) > args.pressure_resident:
@@ -696,6 +709,7 @@ def run_b200(args):
             srv.ensure_async(0, f"m{m}", 1)
         srv.sync(0)
 
+    _phase(rank, t_start, "cache pressure phase done")
     per_rank = None
     fwd_out = ste1["fwd_out_requests"] - ste0["fwd_out_requests"]
     fwd_bytes = (ste1["fwd_peer_bytes_read"] - ste0["fwd_peer_bytes_read"]) + (ste1["fwd_peer_bytes_written"] - ste0["fwd_peer_bytes_written"])
@@ -792,6 +806,7 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()    # nobody closes its window while a peer may still use it
+    _phase(rank, t_start, "line printed, closing")
     if srv is not None:
         srv.close()
     if world > 1:
@@ -908,6 +923,7 @@ def run_reference(args):
 if __name__ == "__main__":
     import faulthandler
     faulthandler.enable()   # a native crash prints the Python stack it happened under
+    faulthandler.dump_traceback_later(600, exit=False)   # a hang leaves the stacks of all threads in stderr (driver limit: 870 s)
     a = parse_args()
     try:
         if a.impl == "reference":

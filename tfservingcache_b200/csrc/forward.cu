@@ -3,6 +3,7 @@
 #include <errno.h>
 #include <poll.h>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <sys/un.h>
 #include <unistd.h>
 
@@ -109,6 +110,14 @@ bool read_msg(int fd, uint8_t* type, std::string* payload) {
   *type = (uint8_t)buf[0];
   payload->assign(buf, 1, std::string::npos);
   return true;
+}
+
+// bound a blocking handshake read (a peer that accepted but never answers must not hang the caller forever)
+void set_rcv_timeout(int fd, double seconds) {
+  timeval tv;
+  tv.tv_sec = (time_t)seconds;
+  tv.tv_usec = (suseconds_t)((seconds - (double)tv.tv_sec) * 1e6);
+  setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
 }
 
 bool make_addr(const std::string& endpoint, sockaddr_un* addr, socklen_t* len, std::string* path_out) {
@@ -279,8 +288,11 @@ Forwarder::~Forwarder() {
   {
     std::lock_guard<std::mutex> lk(conn_mu_);
     for (auto& kv : out_) all.push_back(kv.second);
-    for (auto& c : in_) all.push_back(c);
     out_.clear();
+  }
+  {
+    std::lock_guard<std::mutex> lk(in_mu_);
+    for (auto& c : in_) all.push_back(c);
     in_.clear();
   }
   for (auto& c : all)
@@ -364,6 +376,7 @@ std::shared_ptr<Forwarder::Conn> Forwarder::get_conn(int peer, std::string* err)
   w.raw(&handle_, sizeof handle_);
   uint8_t type = 0;
   std::string payload;
+  set_rcv_timeout(fd, cfg_.timeout_s);
   if (!send_msg(c.get(), MSG_HELLO, w.b) || !read_msg(fd, &type, &payload) || type != MSG_HELLO_ACK) {
     *err = "forward: handshake with rank " + std::to_string(peer) + " failed";
     ::close(fd);
@@ -385,6 +398,7 @@ std::shared_ptr<Forwarder::Conn> Forwarder::get_conn(int peer, std::string* err)
     ::close(fd);
     return nullptr;
   }
+  set_rcv_timeout(fd, 0.0);   // the reader thread blocks until the peer speaks or the socket is shut down
   out_[peer] = c;
   c->reader = std::thread([this, c] { reader_loop(c, false); });
   return c;
@@ -409,10 +423,12 @@ void Forwarder::accept_loop() {
     }
     uint8_t type = 0;
     std::string payload;
+    set_rcv_timeout(fd, 5.0);
     if (!read_msg(fd, &type, &payload) || type != MSG_HELLO) {
       ::close(fd);
       continue;
     }
+    set_rcv_timeout(fd, 0.0);
     Reader r(payload);
     auto c = std::make_shared<Conn>();
     c->fd = fd;
@@ -438,7 +454,7 @@ void Forwarder::accept_loop() {
       continue;
     }
     {
-      std::lock_guard<std::mutex> lk(conn_mu_);
+      std::lock_guard<std::mutex> lk(in_mu_);
       in_.push_back(c);
     }
     c->reader = std::thread([this, c] { reader_loop(c, true); });

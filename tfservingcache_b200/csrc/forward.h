@@ -128,9 +128,10 @@ class Forwarder {
   std::thread acceptor_;
   std::atomic<bool> stop_{false};
 
-  std::mutex conn_mu_;
+  std::mutex conn_mu_;                            // guards out_; HELD ACROSS A DIAL (one dial per peer, like grpcConnMap's write lock)
   std::map<int, std::shared_ptr<Conn>> out_;      // by peer rank
-  std::vector<std::shared_ptr<Conn>> in_;
+  std::mutex in_mu_;                              // guards in_ only: the acceptor must never wait for a dial in progress --
+  std::vector<std::shared_ptr<Conn>> in_;         // with >= 3 ranks dialling each other that closes a cycle (found at N = 8)
 
   std::mutex slot_mu_;
   std::condition_variable slot_cv_;
