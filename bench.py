@@ -415,6 +415,7 @@ def run_b200(args):
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     assert torch.cuda.is_available(), "bench.py needs a B200; the library has no CPU fallback"
     torch.cuda.set_device(local)
+    cpus_total = effective_cpus()          # before the NUMA pinning narrows the affinity mask
     numa = pin_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -442,7 +443,7 @@ def run_b200(args):
         host_gib = min(len(my_models) * model_bytes / 2**30 * 1.02 + 1, avail_kb / 2**20 * 0.7 / max(local_world, 1))
     cfg = {"modelProvider.type": "synthetic", "modelProvider.synthetic.dims": dims,
            "modelProvider.synthetic.count": wl["n_models"], "modelProvider.synthetic.namePrefix": "m",
-           "modelProvider.synthetic.threads": max(1, min(32, effective_cpus() // max(local_world, 1))),
+           "modelProvider.synthetic.threads": max(1, min(32, cpus_total // max(local_world, 1))),
            "gpu.devices": [local], "gpu.arenaBytes": arena, "gpu.maxBatch": 64, "gpu.maxRequestRows": 4096,
            "gpu.stagingSlots": 4, "modelCache.size": int(host_gib * 2**30), "serving.maxConcurrentModels": 1 << 20,
            # routing is done above with the library's ring + picker over the GLOBAL member list (identical on every rank);
@@ -923,7 +924,8 @@ def run_reference(args):
 if __name__ == "__main__":
     import faulthandler
     faulthandler.enable()   # a native crash prints the Python stack it happened under
-    faulthandler.dump_traceback_later(600, exit=False)   # a hang leaves the stacks of all threads in stderr (driver limit: 870 s)
+    # a hang leaves the stacks of all threads in stderr (driver limit per N: 870 s)
+    faulthandler.dump_traceback_later(int(os.environ.get("TFSC_BENCH_DUMP_S", "600")), exit=False)
     a = parse_args()
     try:
         if a.impl == "reference":
