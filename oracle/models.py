@@ -1,8 +1,16 @@
 """Numeric oracle for the executor the reference delegates to (TF-Serving, external and
-unpinned: deploy/docker-compose/docker-compose.yaml:22-37) -- PARITY UNPINNED except for the
-half_plus_two known answer (deploy/docker-compose/readme.md:40-42).  numpy restatement of the
-forward pass of each model template the B200 build executes, reading the same ``weights.bin``
-blob + ``tfsc_model.json`` manifest the product pages into HBM (independent parse).
+unpinned: deploy/docker-compose/docker-compose.yaml:22-37).  TEST INFRASTRUCTURE ONLY: nothing under
+tfservingcache_b200/ imports it.  numpy / torch-CPU restatement of the forward pass of each model
+template the B200 build executes, reading the same ``weights.bin`` blob + ``tfsc_model.json`` manifest
+the product pages into HBM (independent parse).
+
+Pin status: TF-Serving itself cannot run here or on the GPU box, so the only number that comes from it is
+the half_plus_two known answer [1,2,5] -> [2.5,3,4.5] (deploy/docker-compose/readme.md:40-42).  Since
+round 2 the graph templates are pinned on the libraries that DEFINE the two model families instead:
+torchvision's ResNet and transformers' BertForSequenceClassification (seeded, every parameter randomised,
+fp64 forward) are reproduced to 1e-7 / 1e-15 from bundles exported by tests/torch_export.py
+(tests/test_model_pins.py, committed numbers tests/golden/model_torch_golden.json).  The dense-MLP and
+affine templates are plain ``x @ W + b`` / ``a*x + b`` in fp64.
 
 Also holds the seeded synthetic weight generator (integer hash -> uniform fp32), restated
 bit-exactly by the product's synthetic provider (csrc/provider.cc) so that 1 GB models never

@@ -165,6 +165,62 @@ int main(int argc, char** argv) {
       spit(dst + files[k], good_f[k]);
     }
   }
+  // Classify / Regress / SessionRun codecs against bytes serialized from the reference's own schema (argv[5] = directory the
+  // pytest wrapper filled from tests/golden/examples_golden.json), then the same decoders under mutation
+  long ex_ok = 0, ex_runs = 0;
+  if (argc > 5) {
+    const std::string dir = argv[5];
+    auto slurp = [](const std::string& p) { std::string o; FILE* f = fopen(p.c_str(), "rb"); if (f) { char b[4096]; size_t n; while ((n = fread(b, 1, sizeof b, f)) > 0) o.append(b, n); fclose(f); } return o; };
+    const float ys[3] = {2.5f, 3.0f, 4.5f};
+    std::string err;
+    for (const char* kind : {"regress", "classify"}) {
+      const std::string req = slurp(dir + "/" + kind + "_request.bin"), resp = slurp(dir + "/" + kind + "_response.bin");
+      ExampleRequestView v;
+      if (req.empty() || !decode_example_request(req.data(), req.size(), &v, &err) || v.model_name != "half_plus_two" || v.version != 123 ||
+          v.signature_name != std::string(kind) + "_x_to_y" || v.examples.size() != 3) { fprintf(stderr, "%s golden request: decode failed\n", kind); return 1; }
+      const float xs[3] = {1.f, 2.f, 5.f};
+      for (int i = 0; i < 3; ++i) {
+        const std::vector<float>* f = v.examples[i].find("x");
+        if (!f || f->size() != 1 || (*f)[0] != xs[i] || v.examples[i].find("ignored_bytes")) { fprintf(stderr, "%s golden request: features\n", kind); return 1; }
+      }
+      const std::string got = std::string(kind) == "regress" ? encode_regression_response("half_plus_two", 123, "regress_x_to_y", ys, 3)
+                                                              : encode_classification_response("half_plus_two", 123, "classify_x_to_y", ys, 3, 1);
+      if (got != resp) { fprintf(stderr, "%s golden response: bytes differ (%zu vs %zu)\n", kind, got.size(), resp.size()); return 1; }
+    }
+    {  // ExampleListWithContext: the context feature reaches every example
+      const std::string req = slurp(dir + "/regress_with_context_request.bin");
+      ExampleRequestView v;
+      if (!decode_example_request(req.data(), req.size(), &v, &err) || v.examples.size() != 3) { fprintf(stderr, "context request\n"); return 1; }
+      for (auto& e : v.examples) { const std::vector<float>* f = e.find("x"); if (!f || f->size() != 1 || (*f)[0] != 2.f) { fprintf(stderr, "context feature\n"); return 1; } }
+    }
+    const std::string sreq = slurp(dir + "/session_run_request.bin"), sresp = slurp(dir + "/session_run_response.bin");
+    {
+      SessionRunView v;
+      if (!decode_session_run_request(sreq.data(), sreq.size(), &v, &err) || v.model_name != "half_plus_two" || v.version != 123 ||
+          v.feeds.size() != 1 || v.feeds[0].name != "x:0" || v.fetch != std::vector<std::string>{"y:0"}) { fprintf(stderr, "session_run golden request\n"); return 1; }
+      const float* d; int64_t n; std::vector<float> sc;
+      if (!tensor_f32(v.feeds[0], &d, &n, &sc, &err) || n != 3 || d[0] != 1.f || d[2] != 5.f) { fprintf(stderr, "session_run feed tensor\n"); return 1; }
+      std::string prefix, suffix;
+      session_run_response_frame("half_plus_two", 123, "", "y:0", {3}, &prefix, &suffix);
+      const std::string got = prefix + std::string(reinterpret_cast<const char*>(ys), 12) + suffix;
+      if (got != sresp) { fprintf(stderr, "session_run golden response: bytes differ\n"); return 1; }
+    }
+    const std::string good_ex = slurp(dir + "/regress_with_context_request.bin");
+    for (int i = 0; i < iters; ++i) {
+      std::string in = (i % 4 == 0) ? random_bytes(rng() % 200) : mutate((i & 1) ? good_ex : sreq);
+      ExampleRequestView ev; ++ex_runs;
+      if (decode_example_request(in.data(), in.size(), &ev, &err)) {
+        ++ex_ok;
+        volatile float acc = 0;
+        for (auto& e : ev.examples) for (auto& f : e.features) for (float x : f.second) acc += x;
+        (void)acc;
+      }
+      SessionRunView sv;
+      if (decode_session_run_request(in.data(), in.size(), &sv, &err))
+        for (auto& t : sv.feeds) { const float* d; int64_t n; std::vector<float> sc; if (tensor_f32(t, &d, &n, &sc, &err)) { volatile float a2 = 0; for (int64_t k = 0; k < n; ++k) a2 += d[k]; (void)a2; } }
+    }
+  }
+  printf("examples: %ld of %ld mutated Classify/Regress requests decoded\n", ex_ok, ex_runs);
   printf("savedmodel: %ld of %ld mutated imports accepted\n", sm_ok, sm_runs);
   printf("fuzz ok: %d iterations, %ld requests decoded, %ld json parsed, %ld manifests accepted\n", iters, decoded, jsons, manifests);
   return 0;

@@ -30,7 +30,18 @@ def test_host_parsers_survive_fuzzing_under_asan_ubsan(tmp_path):
     os.makedirs(scratch / "variables")
     os.makedirs(tmp_path / "base" / "m")
     os.symlink(fixture, tmp_path / "base" / "m" / "00000007")
-    run = subprocess.run([exe, "20000", str(fixture), str(scratch), str(tmp_path / "base")], capture_output=True, text=True, timeout=300,
+    # Classify / Regress / SessionRun request + response bytes serialized from the reference's schema (tests/golden/examples_golden.json):
+    # the native codec is checked against them here, on the CPU, and then fuzzed
+    import base64
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "examples_golden.json")))
+    exdir = tmp_path / "examples"
+    os.makedirs(exdir)
+    for key in ("regress", "classify", "regress_with_context", "session_run"):
+        for part in ("request", "response"):
+            if part + "_b64" in g[key]:
+                open(exdir / f"{key}_{part}.bin", "wb").write(base64.b64decode(g[key][part + "_b64"]))
+    run = subprocess.run([exe, "20000", str(fixture), str(scratch), str(tmp_path / "base"), str(exdir)], capture_output=True, text=True, timeout=300,
                          env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=1", UBSAN_OPTIONS="print_stacktrace=1"))
     assert run.returncode == 0, (run.stdout + run.stderr)[-4000:]
-    assert "fuzz ok" in run.stdout
+    assert "fuzz ok" in run.stdout and "examples: " in run.stdout
